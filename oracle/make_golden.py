@@ -1,0 +1,112 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+sources (via oracle/ref_loader.py) in the build container.  Run:  python -m oracle.make_golden
+
+Inputs are regenerated from seeds by rap_b200.synth (weights, scenes, injected x_1), so the
+fixtures hold only the reference's outputs plus a checksum of the inputs they belong to.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from oracle.ref_loader import load_reference
+from rap_b200.synth import DiTConfig, make_batch, make_state_dict
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: (num_layers, scenes, views, pts_per_view, steps, rigidity)
+    "cfg1_2x512_s5": (12, 1, 2, 512, 5, False),
+    "cfg1_2x512_s5_rigid": (12, 1, 2, 512, 5, True),
+    "ragged_b2_v3_L2_s3_rigid": (2, 2, 3, [200, 136, 72], 3, True),
+}
+
+
+def input_checksum(batch, sd) -> float:
+    s = float(batch.cond.double().sum() + batch.features.double().sum() + batch.x_1.double().sum())
+    return s + float(sum(v.double().sum() for v in sd.values()))
+
+
+def build_reference_model(ref, cfg: DiTConfig, sd):
+    m = ref.flow_model.PointCloudDiT(in_dim=0, out_dim=3, embed_dim=cfg.embed_dim, num_layers=cfg.num_layers,
+                                     num_heads=cfg.num_heads, attn_dtype="float32", local_feat_dim=cfg.local_feat_dim,
+                                     max_points_per_part=40000, max_points_per_batch=400000)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return m.eval()
+
+
+@torch.inference_mode()
+def run_case(ref, name):
+    L, B, V, N, S, rigid = CASES[name]
+    cfg = DiTConfig(num_layers=L)
+    sd = make_state_dict(cfg, seed=0)
+    batch = make_batch(B, V, N, max_parts=V + 2)     # two padded empty part slots, like max_parts padding
+    model = build_reference_model(ref, cfg, sd)
+    calls = []
+
+    def flow_model_fn(x, t):                          # mirrors modeling.py:672-708
+        ts = torch.full((B,), t)
+        calls.append(t)
+        return model(x=x, timesteps=ts, cond_coord=batch.cond, local_features=batch.features, latent_features=None,
+                     scales=batch.scales, anchor_indices=batch.anchor_indices,
+                     cu_seqlens_batch=batch.cu_seqlens_batch, cu_seqlens_part=batch.cu_seqlens_part)
+
+    t0 = time.perf_counter()
+    res = ref.sampler.get_sampler("euler")(
+        flow_model_fn=flow_model_fn, x_1=batch.x_1, x_0=batch.cond, condition=batch.cond,
+        points_per_part=batch.points_per_part, cu_seqlens_batch=batch.cu_seqlens_batch,
+        anchor_indices=batch.anchor_indices, num_steps=S, return_trajectory=True, rigidity_forcing=rigid,
+        return_end_point_trajectory=True)
+    pred = res["end_point_trajectory"][-1]
+    R, t = ref.procrustes.fit_transformations(batch.cond, pred, batch.points_per_part, batch.cu_seqlens_batch)
+    # one standalone forward with per-scene timesteps and transformer features
+    ts = torch.linspace(0.9, 0.35, B)
+    fwd = model(x=batch.x_1, timesteps=ts, cond_coord=batch.cond, local_features=batch.features, latent_features=None,
+                scales=batch.scales, anchor_indices=batch.anchor_indices, cu_seqlens_batch=batch.cu_seqlens_batch,
+                cu_seqlens_part=batch.cu_seqlens_part, return_transformer_features=True)
+    rigid_once = ref.procrustes.rigidify_prediction_with_procrustes(pred, batch.cond, batch.points_per_part,
+                                                                    batch.cu_seqlens_batch)
+    dt = time.perf_counter() - t0
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        end_point_trajectory=res["end_point_trajectory"].numpy(), trajectory=res["trajectory"].numpy(),
+        rotations=R.numpy(), translations=t.numpy(), fwd_timesteps=ts.numpy(), fwd_velocity=fwd["velocity"].numpy(),
+        fwd_features_checksum=np.float64(fwd["transformer_features"].double().abs().sum()),
+        fwd_features_head=fwd["transformer_features"][:8].numpy(), rigidified=rigid_once.numpy(),
+        input_checksum=np.float64(input_checksum(batch, sd)), call_times=np.array(calls))
+    print(f"{name}: reference ran in {dt:.1f}s, |v|max={fwd['velocity'].abs().max():.3f}")
+
+
+def procrustes_kats(ref):
+    """Known-answer inputs for the rigid fit incl. the det<0 (reflection) branch (procrustes.py:31-33)."""
+    g = torch.Generator("cpu").manual_seed(7)
+    out = {}
+    for i, (n, noise, reflect) in enumerate([(64, 0.0, False), (500, 1e-3, False), (33, 0.0, True), (3, 0.0, False),
+                                             (4096, 5e-2, False)]):
+        src = torch.randn(n, 3, generator=g)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        if (torch.det(q) < 0) != reflect:
+            q[:, 0] *= -1
+        tgt = src @ q.t() + torch.randn(3, generator=g) + noise * torch.randn(n, 3, generator=g)
+        R, t = ref.procrustes.solve_procrustes(src, tgt)
+        out[f"src{i}"], out[f"tgt{i}"], out[f"R{i}"], out[f"t{i}"] = src.numpy(), tgt.numpy(), R.numpy(), t.numpy()
+    np.savez_compressed(os.path.join(OUT, "procrustes_kat.npz"), **out)
+    print("procrustes_kat: done")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    ref = load_reference()
+    procrustes_kats(ref)
+    for name in (sys.argv[1:] or CASES):
+        run_case(ref, name)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the reference's own hot-path modules verbatim.
+
+This file is part of `oracle/`: only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s cpu_baseline / `--impl reference` legs may import it.  It never
+runs on the GPU box (there is no /root/reference there); it exists so that
+`oracle/make_golden.py` can execute the *unmodified* reference sources in the
+build container and pin the restatement in `oracle/rap_oracle.py` against them.
+
+How: the reference package cannot be imported as-is because
+`rectified_point_flow/utils/__init__.py:2` pulls `hydra` and
+`flow_model/layer.py:6` / `norm.py:10` pull `diffusers` and `flash_attn`.  We
+pre-seed `sys.modules` with empty package objects whose `__path__` points at
+the reference directories (so the package `__init__` files never execute) and
+register two third-party shims:
+
+* `diffusers.models.attention.FeedForward`, `diffusers.models.embeddings.
+  {Timesteps, TimestepEmbedding}` -- restated from the published diffusers
+  0.33.0 semantics (pinned only in reference `scripts/install.sh:9`;
+  **unpinned by any reference test** -- see DESIGN.md "parity status").
+* `flash_attn.flash_attn_varlen_qkvpacked_func` -- SDPA per `cu_seqlens`
+  segment, scale 1/sqrt(head_dim), non-causal (reference call sites
+  `flow_model/layer.py:106-111,123-128`).
+
+No reference source is copied; the files are executed where they lie.
+"""
+from __future__ import annotations
+
+import importlib
+import math
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REFERENCE_ROOT = os.environ.get("RAP_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "rectified_point_flow"))
+
+
+# ----------------------------------------------------------------------------
+# third-party shims (diffusers 0.33.0 semantics, flash_attn 2.x semantics)
+# ----------------------------------------------------------------------------
+class _Timesteps(nn.Module):
+    """diffusers.models.embeddings.Timesteps (sinusoidal, no parameters)."""
+
+    def __init__(self, num_channels: int, flip_sin_to_cos: bool, downscale_freq_shift: float, scale: int = 1):
+        super().__init__()
+        self.num_channels = num_channels
+        self.flip_sin_to_cos = flip_sin_to_cos
+        self.downscale_freq_shift = downscale_freq_shift
+        self.scale = scale
+
+    def forward(self, timesteps: torch.Tensor) -> torch.Tensor:
+        half = self.num_channels // 2
+        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device)
+        exponent = exponent / (half - self.downscale_freq_shift)
+        emb = torch.exp(exponent)
+        emb = timesteps[:, None].float() * emb[None, :]
+        emb = self.scale * emb
+        emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+        if self.flip_sin_to_cos:
+            emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+        return emb
+
+
+class _TimestepEmbedding(nn.Module):
+    """diffusers.models.embeddings.TimestepEmbedding: linear_2(SiLU(linear_1(x)))."""
+
+    def __init__(self, in_channels: int, time_embed_dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+    def forward(self, sample: torch.Tensor) -> torch.Tensor:
+        return self.linear_2(self.act(self.linear_1(sample)))
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h, g = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(g)
+
+
+class _FeedForward(nn.Module):
+    """diffusers.models.attention.FeedForward(dim, activation_fn='geglu'), mult=4."""
+
+    def __init__(self, dim: int, dropout: float = 0.0, activation_fn: str = "geglu"):
+        super().__init__()
+        if activation_fn != "geglu":
+            raise NotImplementedError(activation_fn)
+        inner = dim * 4
+        self.net = nn.ModuleList([_GEGLU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim)])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+def _flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None,
+                                      causal=False, window_size=(-1, -1), softcap=0.0, **_):
+    """qkv (total, 3, H, D); exact softmax attention inside each cu_seqlens segment."""
+    assert softcap == 0.0 and not causal
+    total, _, H, D = qkv.shape
+    scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
+    out = torch.empty(total, H, D, dtype=qkv.dtype, device=qkv.device)
+    cu = cu_seqlens.tolist()
+    for s, e in zip(cu[:-1], cu[1:]):
+        if e == s:
+            continue
+        q, k, v = (qkv[s:e, i].transpose(0, 1) for i in range(3))  # (H, n, D)
+        out[s:e] = F.scaled_dot_product_attention(q[None], k[None], v[None], scale=scale)[0].transpose(0, 1)
+    return out
+
+
+def _install_shims() -> None:
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    if "diffusers" not in sys.modules:
+        mod("diffusers").__path__ = []
+        mod("diffusers.models").__path__ = []
+        mod("diffusers.models.attention", FeedForward=_FeedForward)
+        mod("diffusers.models.embeddings", Timesteps=_Timesteps, TimestepEmbedding=_TimestepEmbedding)
+    # Always shadow flash_attn on CPU: the real wheel is CUDA-only at run time.
+    fa = types.ModuleType("flash_attn")
+    fa.flash_attn_varlen_qkvpacked_func = _flash_attn_varlen_qkvpacked_func
+    sys.modules["flash_attn"] = fa
+
+
+_PKG = "rectified_point_flow"
+
+
+def load_reference():
+    """Returns a namespace with the reference's own `sampler`, `procrustes`,
+    `point_clouds` and `flow_model` modules (executed verbatim)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    _install_shims()
+    root = os.path.join(REFERENCE_ROOT, _PKG)
+    for name, path in ((_PKG, root), (_PKG + ".utils", os.path.join(root, "utils"))):
+        if name not in sys.modules or not getattr(sys.modules[name], "_rap_bypass", False):
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            m._rap_bypass = True
+            sys.modules[name] = m
+    ns = types.SimpleNamespace()
+    ns.point_clouds = importlib.import_module(_PKG + ".utils.point_clouds")
+    ns.procrustes = importlib.import_module(_PKG + ".procrustes")
+    ns.sampler = importlib.import_module(_PKG + ".sampler")
+    ns.flow_model = importlib.import_module(_PKG + ".flow_model")
+    return ns
+
+
+def unload_reference() -> None:
+    """Remove the bypass packages so `rap_b200.install()` can be tested after."""
+    for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:
+        del sys.modules[k]
