@@ -1,0 +1,96 @@
+/* rap_b200 -- C ABI of the B200-native flow-matching registration sampler (PRBonn/RAP hot path).
+ *
+ * The reference has no FFI/plugin registry; its drop-in boundary is three Python modules
+ * (SURVEY.md 8(b)).  The Python mirrors in rap_b200/rectified_point_flow/ bind exactly these entry
+ * points with ctypes; each one names the reference interface it replaces (paths relative to
+ * /root/reference/rectified_point_flow).
+ *
+ * Conventions: all tensor pointers are DEVICE pointers borrowed from the caller (row-major, contiguous,
+ * kept alive until the stream has run); fp32 for coordinates/poses, int32 for offsets; `stream` is a
+ * cudaStream_t passed as void*.  No entry point synchronises the host except where stated.  Return 0 on
+ * success or a negative errno-style code, with a message available from rap_last_error().
+ */
+#ifndef RAP_B200_H
+#define RAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rap_dit rap_dit_t;   /* packed PointCloudDiT weights on one device                  */
+typedef struct rap_plan rap_plan_t; /* batch layout (cu_seqlens), workspace, tensor maps, tile lists */
+
+int rap_version(void);
+const char* rap_last_error(void);
+/* Reads (and clears) the device-side protocol error word; host-synchronising, for tests. 0 = clean. */
+int rap_device_error(unsigned int* code_out);
+
+/* ---- model: replaces flow_model.PointCloudDiT (flow_model/point_cloud_dit.py:10-117) -------------- */
+int rap_dit_create(rap_dit_t** out, int embed_dim, int num_layers, int num_heads, int local_feat_dim);
+void rap_dit_destroy(rap_dit_t* dit);
+/* `key` is the reference state_dict key; `src` a device fp32 tensor of `numel`
+ * elements in the reference layout.  The library converts / re-packs it (fp16 operands, GEGLU row
+ * interleave, emb_proj column split). */
+int rap_dit_load_weight(rap_dit_t* dit, const char* key, const float* src, int64_t numel, void* stream);
+/* Fails unless every key of the reference state_dict has been loaded exactly as shaped. */
+int rap_dit_finalize(rap_dit_t* dit);
+int rap_dit_num_keys(const rap_dit_t* dit);
+const char* rap_dit_key(const rap_dit_t* dit, int index, int64_t* numel_out);
+
+/* ---- batch plan: replaces RectifiedPointFlow._prepare_data (modeling.py:203-231) ------------------
+ * cu_seqlens_batch: HOST int32 [n_scenes+1]; points_per_part: HOST int32 [n_scenes*max_parts]
+ * (zero = empty slot).  max_timesteps bounds num_steps of rap_sample_euler / n_scenes of rap_dit_forward. */
+int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, const int32_t* cu_seqlens_batch,
+                    const int32_t* points_per_part, int max_parts, int max_timesteps);
+void rap_plan_destroy(rap_plan_t* plan);
+int rap_plan_tokens(const rap_plan_t* plan);
+int rap_plan_valid_parts(const rap_plan_t* plan);
+/* Step-invariant inputs (cond (T,3) f32, local_features (T,F) f32, scales (n_scenes) f32, anchor (T) u8):
+ * evaluates the step-invariant half of the embedding once (embedding.py:155-177 minus the x_t term). */
+int rap_plan_set_condition(rap_plan_t* plan, const float* cond, const float* local_features, const float* scales,
+                           const uint8_t* anchor_indices, void* stream);
+
+/* PointCloudDiT.forward (point_cloud_dit.py:141-191): velocity (T,3) f32; transformer_features (T,512) f32
+ * or NULL.  timesteps: device f32 [n_scenes]. */
+int rap_dit_forward(rap_plan_t* plan, const float* x, const float* timesteps, float* velocity,
+                    float* transformer_features, void* stream);
+
+/* get_sampler('euler') / flow_sampler (sampler.py:11-92) fused with the model: all num_steps Euler steps
+ * with x_t resident on the device.  end_point_trajectory / trajectory: (num_steps,T,3) f32 or NULL;
+ * x_final: (T,3) f32 or NULL; transformer_features: (T,512) of the last step or NULL. */
+int rap_sample_euler(rap_plan_t* plan, const float* x_1, int num_steps, int rigidity_forcing,
+                     float* end_point_trajectory, float* trajectory, float* x_final,
+                     float* transformer_features, void* stream);
+
+/* ---- Procrustes: replaces procrustes.py:40-118 --------------------------------------------------
+ * cu_seqlens_part: device int32 [n_parts+1] over the packed (T,3) clouds; slot: device int32 [n_parts]
+ * giving b*max_parts+p of each non-empty part (NULL = identity).  rotations (slots,3,3) / translations
+ * (slots,3) must be zero-initialised by the caller so empty slots read as zeros (procrustes.py:71-76). */
+int rap_procrustes_fit(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot,
+                       int n_parts, float* rotations, float* translations, void* stream);
+/* out = (R cond + t) * w_rigid + mix * w_mix per part, (R,t) fitted cond -> prediction; mix may be NULL.
+ * rigidify_prediction_with_procrustes is w_rigid=1, mix=NULL; sampler.py:60 is w_rigid=1-t+dt, w_mix=t-dt. */
+int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_seqlens_part, int n_parts,
+                            float* out, const float* mix, float w_rigid, float w_mix, void* stream);
+/* Plan-bound convenience wrappers using the plan's own part table. */
+int rap_plan_fit(rap_plan_t* plan, const float* source, const float* target, float* rotations, float* translations, void* stream);
+int rap_plan_rigidify(rap_plan_t* plan, const float* prediction, const float* condition, float* out, void* stream);
+
+/* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
+int rap_kabsch_host(const double* H9, double* R9);
+
+/* Kernel launch counter (incremented by every kernel this library launches; for bench.py's gpu_launches). */
+int64_t rap_launch_count(void);
+
+/* Micro entry points used by tests/ and profiling to exercise one kernel at a time. */
+int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
+                  const float* addend, float* out32, void* out16, const float* gamma, void* stream);
+int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out_f16,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAP_B200_H */

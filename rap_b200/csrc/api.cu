@@ -1,0 +1,585 @@
+// C ABI (include/rap_b200.h): weight packing, batch plans, the DiT forward schedule, the fused Euler
+// sampler and the Procrustes entry points.  Host code only enqueues kernels on the caller's stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rap_b200.h"
+#include "fmha.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace rap {
+
+__device__ unsigned int g_dev_error = 0;
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+void note_launch(int n) { g_launches += n; }
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library links (and loads on a CPU-only
+// box) without libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(RAP_ENODEV, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    RAP_REQUIRE(box_rows >= 1 && box_rows <= 256 && cols % 64 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+                "tensor map: bad geometry rows=%llu cols=%llu box_rows=%u", (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RAP_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return RAP_OK;
+}
+
+}  // namespace rap
+
+using namespace rap;
+
+// ======================================================================================= model
+namespace {
+
+constexpr int D = 512, HEADS = 8, HD = 64, FF_INNER = 2048, ADA_CH = 256;
+
+struct WeightEntry {
+    void* dst = nullptr;
+    bool half = false;
+    PackSpec spec{};
+    int64_t src_numel = 0;
+    bool loaded = false;
+};
+
+struct Slab {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    template <typename T> T* take(size_t n) {
+        used = (used + 255) & ~size_t(255);
+        T* p = reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace
+
+struct rap_dit {
+    int L = 0, F = 0, M = 0;   // layers, local feature dim, AdaLN modules (2 per layer)
+    int device = 0;
+    Slab slab;
+    // embedding
+    __half *w_emb_x = nullptr, *w_emb_s = nullptr;
+    float *b_emb = nullptr, *anchor_emb = nullptr;
+    // per layer
+    std::vector<__half*> wqkv[2], wout[2], w1, w2;
+    std::vector<float*> bout[2], gamma[2] /* [2(q,k),8,64] */, b1, b2, ffn_w, ffn_b;
+    // AdaLN MLPs, module m = 2*layer + blk
+    __half *ada_w1 = nullptr, *ada_w2 = nullptr, *ada_w3 = nullptr;
+    float *ada_b1 = nullptr, *ada_b2 = nullptr, *ada_b3 = nullptr;
+    // head
+    __half *wh0 = nullptr, *wh2 = nullptr;
+    float *bh0 = nullptr, *bh2 = nullptr, *wh4 = nullptr;
+    // B-operand tensor maps
+    CUtensorMap tm_emb_x, tm_emb_s, tm_h0, tm_h2;
+    std::vector<CUtensorMap> tm_qkv[2], tm_out[2], tm_w1, tm_w2;
+    std::map<std::string, WeightEntry> entries;
+    std::vector<std::string> key_order;
+    bool finalized = false;
+};
+
+namespace {
+
+PackSpec plain(int rows, int cols) {
+    PackSpec s{};
+    s.rows = rows; s.cols = cols; s.src_ld = cols; s.row_mode = 0; s.n_ranges = 1; s.range_start[0] = 0; s.range_len[0] = cols;
+    return s;
+}
+
+void add_entry(rap_dit* d, const std::string& key, void* dst, bool half, const PackSpec& spec, int64_t src_numel) {
+    WeightEntry e;
+    e.dst = dst; e.half = half; e.spec = spec; e.src_numel = src_numel;
+    d->entries[key] = e;
+    d->key_order.push_back(key);
+}
+
+}  // namespace
+
+extern "C" int rap_version(void) { return 100; }
+extern "C" const char* rap_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t rap_launch_count(void) { return g_launches.load(); }
+
+extern "C" int rap_device_error(unsigned int* code_out) {
+    unsigned int code = 0, zero = 0;
+    RAP_CUDA(cudaDeviceSynchronize());
+    RAP_CUDA(cudaMemcpyFromSymbol(&code, g_dev_error, sizeof code));
+    if (code) RAP_CUDA(cudaMemcpyToSymbol(g_dev_error, &zero, sizeof zero));
+    if (code_out) *code_out = code;
+    return RAP_OK;
+}
+
+extern "C" int rap_dit_create(rap_dit_t** out, int embed_dim, int num_layers, int num_heads, int local_feat_dim) {
+    RAP_REQUIRE(out, "rap_dit_create: out is NULL");
+    RAP_REQUIRE(embed_dim == D && num_heads == HEADS, "rap_dit_create: the sm_100a kernels are specialised for embed_dim=512, 8 heads of 64 (got %d, %d)", embed_dim, num_heads);
+    RAP_REQUIRE(num_layers >= 1 && num_layers <= 64 && local_feat_dim >= 0 && local_feat_dim <= 44, "rap_dit_create: bad num_layers/local_feat_dim");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RAP_ENODEV, "rap_dit_create: no CUDA device (this library has no CPU fallback)");
+    rap_dit* d = new rap_dit();
+    d->L = num_layers; d->F = local_feat_dim; d->M = 2 * num_layers;
+    cudaGetDevice(&d->device);
+    const int L = d->L, M = d->M;
+    size_t halfs = (size_t)D * 64 + (size_t)D * 128 + (size_t)L * (2 * 3 * D * D + 2 * D * D + 2 * FF_INNER * D + D * FF_INNER) +
+                   (size_t)M * (D * ADA_CH + D * D + 2 * D * D) + (size_t)D * D + (size_t)(D / 2) * D;
+    size_t floats = (size_t)D + 2 * D + (size_t)L * (2 * D + 2 * 2 * HEADS * HD + 2 * FF_INNER + D + 2 * D) + (size_t)M * (D + D + 2 * D) + D + D / 2 + 3 * (D / 2);
+    d->slab.size = halfs * 2 + floats * 4 + 256 * (64 + 20 * (size_t)L);
+    if (cudaMalloc(&d->slab.base, d->slab.size) != cudaSuccess) { delete d; return fail(RAP_ENOMEM, "rap_dit_create: cudaMalloc(%zu) failed", d->slab.size); }
+    cudaMemset(d->slab.base, 0, d->slab.size);
+    Slab& s = d->slab;
+    const int EIN = 126 + 21 + d->F;   // 63 + 63 + 21 + F
+
+    d->w_emb_x = s.take<__half>((size_t)D * 64);
+    d->w_emb_s = s.take<__half>((size_t)D * 128);
+    d->b_emb = s.take<float>(D);
+    d->anchor_emb = s.take<float>(2 * D);
+    add_entry(d, "anchor_part_emb.weight", d->anchor_emb, false, plain(2, D), 2 * D);
+    {   // emb_proj.weight (512, 179): columns [cond 0:63 | x_t 63:126 | scale 126:147 | feat 147:179] (embedding.py:161-177)
+        PackSpec sx{}; sx.rows = D; sx.cols = 64; sx.src_ld = EIN; sx.n_ranges = 1; sx.range_start[0] = 63; sx.range_len[0] = 63;
+        PackSpec ss{}; ss.rows = D; ss.cols = 128; ss.src_ld = EIN; ss.n_ranges = 3;
+        ss.range_start[0] = 0; ss.range_len[0] = 63; ss.range_start[1] = 126; ss.range_len[1] = 21; ss.range_start[2] = 147; ss.range_len[2] = d->F;
+        add_entry(d, "encoding_manager.emb_proj.weight", d->w_emb_x, true, sx, (int64_t)D * EIN);
+        add_entry(d, "encoding_manager.emb_proj.weight#static", d->w_emb_s, true, ss, (int64_t)D * EIN);
+    }
+    add_entry(d, "encoding_manager.emb_proj.bias", d->b_emb, false, plain(1, D), D);
+
+    d->ada_w1 = s.take<__half>((size_t)M * D * ADA_CH); d->ada_b1 = s.take<float>((size_t)M * D);
+    d->ada_w2 = s.take<__half>((size_t)M * D * D);      d->ada_b2 = s.take<float>((size_t)M * D);
+    d->ada_w3 = s.take<__half>((size_t)M * 2 * D * D);  d->ada_b3 = s.take<float>((size_t)M * 2 * D);
+
+    const char* blk_name[2] = {"self", "global"};
+    for (int l = 0; l < L; ++l) {
+        const std::string p = "transformer_layers." + std::to_string(l) + ".";
+        for (int b = 0; b < 2; ++b) {
+            const int m = 2 * l + b;
+            const std::string q = p + blk_name[b];
+            add_entry(d, q + "_prenorm.timestep_embedder.linear_1.weight", d->ada_w1 + (size_t)m * D * ADA_CH, true, plain(D, ADA_CH), (int64_t)D * ADA_CH);
+            add_entry(d, q + "_prenorm.timestep_embedder.linear_1.bias", d->ada_b1 + (size_t)m * D, false, plain(1, D), D);
+            add_entry(d, q + "_prenorm.timestep_embedder.linear_2.weight", d->ada_w2 + (size_t)m * D * D, true, plain(D, D), (int64_t)D * D);
+            add_entry(d, q + "_prenorm.timestep_embedder.linear_2.bias", d->ada_b2 + (size_t)m * D, false, plain(1, D), D);
+            add_entry(d, q + "_prenorm.linear.weight", d->ada_w3 + (size_t)m * 2 * D * D, true, plain(2 * D, D), (int64_t)2 * D * D);
+            add_entry(d, q + "_prenorm.linear.bias", d->ada_b3 + (size_t)m * 2 * D, false, plain(1, 2 * D), 2 * D);
+            d->wqkv[b].push_back(s.take<__half>((size_t)3 * D * D));
+            d->wout[b].push_back(s.take<__half>((size_t)D * D));
+            d->bout[b].push_back(s.take<float>(D));
+            d->gamma[b].push_back(s.take<float>(2 * HEADS * HD));
+            add_entry(d, q + "_qkv_proj.weight", d->wqkv[b][l], true, plain(3 * D, D), (int64_t)3 * D * D);
+            add_entry(d, q + "_out_proj.weight", d->wout[b][l], true, plain(D, D), (int64_t)D * D);
+            add_entry(d, q + "_out_proj.bias", d->bout[b][l], false, plain(1, D), D);
+            add_entry(d, q + "_q_norm.gamma", d->gamma[b][l], false, plain(HEADS, HD), HEADS * HD);
+            add_entry(d, q + "_k_norm.gamma", d->gamma[b][l] + HEADS * HD, false, plain(HEADS, HD), HEADS * HD);
+        }
+        d->ffn_w.push_back(s.take<float>(D)); d->ffn_b.push_back(s.take<float>(D));
+        d->w1.push_back(s.take<__half>((size_t)2 * FF_INNER * D)); d->b1.push_back(s.take<float>(2 * FF_INNER));
+        d->w2.push_back(s.take<__half>((size_t)D * FF_INNER)); d->b2.push_back(s.take<float>(D));
+        add_entry(d, p + "ff_norm.weight", d->ffn_w[l], false, plain(1, D), D);
+        add_entry(d, p + "ff_norm.bias", d->ffn_b[l], false, plain(1, D), D);
+        PackSpec g = plain(2 * FF_INNER, D); g.row_mode = 1;          // [h rows | g rows] -> 128/128 interleave per 256-wide tile
+        PackSpec gb{}; gb.rows = 2 * FF_INNER; gb.cols = 1; gb.src_ld = 1; gb.row_mode = 1; gb.n_ranges = 1; gb.range_start[0] = 0; gb.range_len[0] = 1;
+        add_entry(d, p + "ff.net.0.proj.weight", d->w1[l], true, g, (int64_t)2 * FF_INNER * D);
+        add_entry(d, p + "ff.net.0.proj.bias", d->b1[l], false, gb, 2 * FF_INNER);
+        add_entry(d, p + "ff.net.2.weight", d->w2[l], true, plain(D, FF_INNER), (int64_t)D * FF_INNER);
+        add_entry(d, p + "ff.net.2.bias", d->b2[l], false, plain(1, D), D);
+    }
+    d->wh0 = s.take<__half>((size_t)D * D); d->bh0 = s.take<float>(D);
+    d->wh2 = s.take<__half>((size_t)(D / 2) * D); d->bh2 = s.take<float>(D / 2);
+    d->wh4 = s.take<float>(3 * (D / 2));
+    add_entry(d, "final_mlp.0.weight", d->wh0, true, plain(D, D), (int64_t)D * D);
+    add_entry(d, "final_mlp.0.bias", d->bh0, false, plain(1, D), D);
+    add_entry(d, "final_mlp.2.weight", d->wh2, true, plain(D / 2, D), (int64_t)(D / 2) * D);
+    add_entry(d, "final_mlp.2.bias", d->bh2, false, plain(1, D / 2), D / 2);
+    add_entry(d, "final_mlp.4.weight", d->wh4, false, plain(3, D / 2), 3 * (D / 2));
+    if (s.used > s.size) { cudaFree(s.base); delete d; return fail(RAP_ESTATE, "rap_dit_create: slab overflow (%zu > %zu)", s.used, s.size); }
+    *out = d;
+    return RAP_OK;
+}
+
+extern "C" void rap_dit_destroy(rap_dit_t* d) {
+    if (!d) return;
+    cudaFree(d->slab.base);
+    delete d;
+}
+
+extern "C" int rap_dit_num_keys(const rap_dit_t* d) {
+    int n = 0;
+    for (auto& k : d->key_order) n += (k.find('#') == std::string::npos);
+    return n;
+}
+extern "C" const char* rap_dit_key(const rap_dit_t* d, int index, int64_t* numel_out) {
+    int n = 0;
+    for (auto& k : d->key_order) {
+        if (k.find('#') != std::string::npos) continue;
+        if (n++ == index) {
+            if (numel_out) *numel_out = d->entries.at(k).src_numel;
+            return k.c_str();
+        }
+    }
+    return nullptr;
+}
+
+extern "C" int rap_dit_load_weight(rap_dit_t* d, const char* key, const float* src, int64_t numel, void* stream) {
+    RAP_REQUIRE(d && key && src, "rap_dit_load_weight: NULL argument");
+    auto it = d->entries.find(key);
+    RAP_REQUIRE(it != d->entries.end() && std::string(key).find('#') == std::string::npos, "rap_dit_load_weight: unexpected key '%s'", key);
+    RAP_REQUIRE(numel == it->second.src_numel, "rap_dit_load_weight: '%s' has %lld elements, expected %lld", key, (long long)numel, (long long)it->second.src_numel);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RAP_TRY(launch_pack(src, it->second.dst, it->second.half, it->second.spec, st));
+    it->second.loaded = true;
+    auto aux = d->entries.find(std::string(key) + "#static");
+    if (aux != d->entries.end()) {
+        RAP_TRY(launch_pack(src, aux->second.dst, aux->second.half, aux->second.spec, st));
+        aux->second.loaded = true;
+    }
+    d->finalized = false;
+    return RAP_OK;
+}
+
+extern "C" int rap_dit_finalize(rap_dit_t* d) {
+    RAP_REQUIRE(d, "rap_dit_finalize: NULL");
+    for (auto& kv : d->entries)
+        if (!kv.second.loaded) return fail(RAP_ESTATE, "rap_dit_finalize: missing key '%s'", kv.first.c_str());
+    const int L = d->L;
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_x, d->w_emb_x, D, 64, 64, 128));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_s, d->w_emb_s, D, 128, 128, 128));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_h0, d->wh0, D, D, D, 128));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_h2, d->wh2, D / 2, D, D, 128));
+    for (int b = 0; b < 2; ++b) { d->tm_qkv[b].resize(L); d->tm_out[b].resize(L); }
+    d->tm_w1.resize(L); d->tm_w2.resize(L);
+    for (int l = 0; l < L; ++l) {
+        for (int b = 0; b < 2; ++b) {
+            RAP_TRY(make_tmap_f16_sw128(&d->tm_qkv[b][l], d->wqkv[b][l], 3 * D, D, D, 256));
+            RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, 128));
+        }
+        RAP_TRY(make_tmap_f16_sw128(&d->tm_w1[l], d->w1[l], 2 * FF_INNER, D, D, 256));
+        RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, 128));
+    }
+    d->finalized = true;
+    return RAP_OK;
+}
+
+// ======================================================================================= plan
+struct rap_plan {
+    rap_dit* dit = nullptr;
+    int T = 0, B = 0, P = 0, VP = 0, n_cap = 0;
+    int n_tiles_part = 0, n_tiles_batch = 0;
+    char* ws = nullptr;
+    // layout
+    int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr;
+    int4 *tiles_part = nullptr, *tiles_batch = nullptr;
+    // activations
+    float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
+    __half *x16 = nullptr, *attn16 = nullptr, *qkv = nullptr, *ffmid = nullptr, *a_s = nullptr, *a_x = nullptr, *hh16 = nullptr, *y1 = nullptr, *y2 = nullptr;
+    float *ada_e0 = nullptr, *ada_e1 = nullptr, *ada_e2 = nullptr, *ada_tab = nullptr;
+    CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn;
+    const float* cond = nullptr;
+    const uint8_t* anchor = nullptr;
+    bool condition_set = false;
+};
+
+namespace {
+
+__global__ void sampler_timesteps_kernel(float* t, int num_steps) {   // t_i = 1 - i * (1/num_steps), rounded like float(python double)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_steps) t[i] = (float)(1.0 - (double)i * (1.0 / (double)num_steps));
+}
+
+void build_tiles(const std::vector<int>& cu, std::vector<int4>& tiles) {
+    for (size_t s = 0; s + 1 < cu.size(); ++s)
+        for (int q = cu[s]; q < cu[s + 1]; q += 128) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
+}
+
+}  // namespace
+
+extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, const int32_t* cu_b, const int32_t* ppp, int max_parts, int max_timesteps) {
+    RAP_REQUIRE(out && dit && cu_b && ppp, "rap_plan_create: NULL argument");
+    RAP_REQUIRE(dit->finalized, "rap_plan_create: call rap_dit_finalize first");
+    RAP_REQUIRE(n_scenes >= 1 && max_parts >= 1 && cu_b[0] == 0, "rap_plan_create: bad layout");
+    const int T = cu_b[n_scenes];
+    RAP_REQUIRE(T >= 1, "rap_plan_create: empty batch");
+    std::vector<int> cu_batch(cu_b, cu_b + n_scenes + 1), cu_part{0}, slot, scene_of_tok(T);
+    for (int b = 0; b < n_scenes; ++b) {
+        RAP_REQUIRE(cu_b[b + 1] >= cu_b[b], "rap_plan_create: cu_seqlens_batch not monotone");
+        int sum = 0;
+        for (int p = 0; p < max_parts; ++p) {
+            const int n = ppp[b * max_parts + p];
+            RAP_REQUIRE(n >= 0, "rap_plan_create: negative points_per_part");
+            if (n > 0) { cu_part.push_back(cu_part.back() + n); slot.push_back(b * max_parts + p); }
+            sum += n;
+        }
+        // same invariant the reference asserts in utils/point_clouds.py:41-44
+        RAP_REQUIRE(sum == cu_b[b + 1] - cu_b[b], "rap_plan_create: sum(points_per_part[%d])=%d != scene length %d", b, sum, cu_b[b + 1] - cu_b[b]);
+        for (int i = cu_b[b]; i < cu_b[b + 1]; ++i) scene_of_tok[i] = b;
+    }
+    std::vector<int4> tp, tb;
+    build_tiles(cu_part, tp);
+    build_tiles(cu_batch, tb);
+
+    rap_plan* pl = new rap_plan();
+    pl->dit = dit; pl->T = T; pl->B = n_scenes; pl->P = max_parts; pl->VP = (int)slot.size();
+    pl->n_cap = std::max(std::max(max_timesteps, n_scenes), 1);
+    pl->n_tiles_part = (int)tp.size(); pl->n_tiles_batch = (int)tb.size();
+    const int M = dit->M;
+    const size_t Tp = (size_t)((T + 127) / 128) * 128;     // padded rows so tail tiles stay in-bounds for plain loads/stores
+    size_t bytes = 0;
+    auto need = [&](size_t n) { bytes = ((bytes + 255) & ~size_t(255)) + n; };
+    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(16 * tp.size()); need(16 * tb.size());
+    need(4 * Tp * D); need(4 * Tp * D); need(4 * Tp * 3); need(4 * (size_t)pl->n_cap);
+    need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * 3 * D); need(2 * Tp * FF_INNER); need(2 * Tp * 128); need(2 * Tp * 64);
+    need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * (D / 2));
+    need(4 * (size_t)pl->n_cap * ADA_CH); need(4 * (size_t)pl->n_cap * M * D); need(4 * (size_t)pl->n_cap * M * D); need(4 * (size_t)pl->n_cap * M * 2 * D);
+    bytes += 4096;
+    if (cudaMalloc(&pl->ws, bytes) != cudaSuccess) { delete pl; return fail(RAP_ENOMEM, "rap_plan_create: cudaMalloc(%zu) failed", bytes); }
+    cudaMemset(pl->ws, 0, bytes);
+    Slab s; s.base = pl->ws; s.size = bytes;
+    pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T);
+    pl->tiles_part = s.take<int4>(tp.size()); pl->tiles_batch = s.take<int4>(tb.size());
+    pl->h = s.take<float>(Tp * D); pl->h_static = s.take<float>(Tp * D); pl->x_t = s.take<float>(Tp * 3); pl->tbuf = s.take<float>(pl->n_cap);
+    pl->x16 = s.take<__half>(Tp * D); pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
+    pl->a_s = s.take<__half>(Tp * 128); pl->a_x = s.take<__half>(Tp * 64);
+    pl->hh16 = s.take<__half>(Tp * D); pl->y1 = s.take<__half>(Tp * D); pl->y2 = s.take<__half>(Tp * (D / 2));
+    pl->ada_e0 = s.take<float>((size_t)pl->n_cap * ADA_CH); pl->ada_e1 = s.take<float>((size_t)pl->n_cap * M * D);
+    pl->ada_e2 = s.take<float>((size_t)pl->n_cap * M * D); pl->ada_tab = s.take<float>((size_t)pl->n_cap * M * 2 * D);
+    if (s.used > s.size) { cudaFree(pl->ws); delete pl; return fail(RAP_ESTATE, "rap_plan_create: workspace overflow"); }
+    auto up = [&](void* dst, const void* src, size_t n) { return n == 0 ? cudaSuccess : cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
+    cudaError_t e = up(pl->cu_part, cu_part.data(), 4 * cu_part.size());
+    if (e == cudaSuccess) e = up(pl->slot, slot.data(), 4 * slot.size());
+    if (e == cudaSuccess) e = up(pl->scene_of_tok, scene_of_tok.data(), 4 * (size_t)T);
+    if (e == cudaSuccess) e = up(pl->tiles_part, tp.data(), 16 * tp.size());
+    if (e == cudaSuccess) e = up(pl->tiles_batch, tb.data(), 16 * tb.size());
+    int rc = e == cudaSuccess ? RAP_OK : fail(RAP_ECUDA, "rap_plan_create: upload failed: %s", cudaGetErrorString(e));
+    // A-operand tensor maps (rows = T so out-of-range rows of the last tile are zero-filled by TMA)
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_x16, pl->x16, T, D, D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_attn16, pl->attn16, T, D, D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_ffmid, pl->ffmid, T, FF_INNER, FF_INNER, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_as, pl->a_s, T, 128, 128, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_ax, pl->a_x, T, 64, 64, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_hh16, pl->hh16, T, D, D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_y1, pl->y1, T, D, D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_qkv_attn, pl->qkv, T, 3 * D, 3 * D, 128);
+    if (rc) { cudaFree(pl->ws); delete pl; return rc; }
+    *out = pl;
+    return RAP_OK;
+}
+
+extern "C" void rap_plan_destroy(rap_plan_t* pl) {
+    if (!pl) return;
+    cudaFree(pl->ws);
+    delete pl;
+}
+extern "C" int rap_plan_tokens(const rap_plan_t* pl) { return pl ? pl->T : 0; }
+extern "C" int rap_plan_valid_parts(const rap_plan_t* pl) { return pl ? pl->VP : 0; }
+
+extern "C" int rap_plan_set_condition(rap_plan_t* pl, const float* cond, const float* feats, const float* scales, const uint8_t* anchor, void* stream) {
+    RAP_REQUIRE(pl && cond && scales && anchor && (feats || pl->dit->F == 0), "rap_plan_set_condition: NULL argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rap_dit* d = pl->dit;
+    RAP_TRY(launch_posenc_static(cond, scales, pl->scene_of_tok, feats, d->F, pl->a_s, pl->T, st));
+    GemmArgs g{};
+    g.M = pl->T; g.N = D; g.K = 128; g.bias = d->b_emb; g.out32 = pl->h_static; g.ld32 = D; g.table = d->anchor_emb; g.sel = anchor;
+    RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_as, d->tm_emb_s, g, st));
+    pl->cond = cond; pl->anchor = anchor; pl->condition_set = true;
+    return RAP_OK;
+}
+
+namespace {
+
+// AdaLN scale/shift for n timesteps already in pl->tbuf: table[n][module][scale 512 | shift 512]
+int ada_table(rap_plan* pl, int n, cudaStream_t st) {
+    rap_dit* d = pl->dit;
+    RAP_TRY(launch_timestep_sincos(pl->tbuf, pl->ada_e0, n, st));
+    RAP_TRY(launch_ada_linear(d->ada_w1, d->ada_b1, pl->ada_e0, 0, pl->ada_e1, n, d->M, D, ADA_CH, 1, st));
+    RAP_TRY(launch_ada_linear(d->ada_w2, d->ada_b2, pl->ada_e1, 1, pl->ada_e2, n, d->M, D, D, 1, st));
+    RAP_TRY(launch_ada_linear(d->ada_w3, d->ada_b3, pl->ada_e2, 1, pl->ada_tab, n, d->M, 2 * D, D, 0, st));
+    return RAP_OK;
+}
+
+// One velocity evaluation.  x: (T,3).  tab_row0: first row of the AdaLN table for this call; per_scene: rows indexed by scene.
+// Leaves y2 (T,256) ready for the head tail; h holds the transformer features.
+int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStream_t st) {
+    rap_dit* d = pl->dit;
+    const int T = pl->T, M = d->M;
+    const float scale_log2 = 1.4426950408889634f / 8.0f;   // log2(e) / sqrt(64)
+    RAP_TRY(launch_posenc_x(x, pl->a_x, T, st));
+    {
+        GemmArgs g{};
+        g.M = T; g.N = D; g.K = 64; g.addend = pl->h_static; g.out32 = pl->h; g.ld32 = D;
+        RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_ax, d->tm_emb_x, g, st));
+    }
+    const int row_stride = M * 2 * D;
+    for (int l = 0; l < d->L; ++l) {
+        for (int b = 0; b < 2; ++b) {
+            const float* ss = pl->ada_tab + ((size_t)tab_row0 * M + (2 * l + b)) * 2 * D;
+            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, ss, ss + D, row_stride, per_scene ? pl->scene_of_tok : nullptr, 1.0f, st));
+            GemmArgs q{};
+            q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
+            RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
+            FmhaArgs f{};
+            f.tiles = b == 0 ? pl->tiles_part : pl->tiles_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
+            RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_tiles_part : pl->n_tiles_batch, HEADS, st));
+            GemmArgs o{};
+            o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
+            RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_attn16, d->tm_out[b][l], o, st));
+        }
+        RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, nullptr, 0.0f, st));
+        GemmArgs f1{};
+        f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER;
+        RAP_TRY(launch_gemm(EPI_GEGLU, 256, pl->tm_x16, d->tm_w1[l], f1, st));
+        GemmArgs f2{};
+        f2.M = T; f2.N = D; f2.K = FF_INNER; f2.bias = d->b2[l]; f2.addend = pl->h; f2.out32 = pl->h; f2.ld32 = D;
+        if (l == d->L - 1) { f2.out16 = pl->hh16; f2.ld16 = D; }
+        RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_ffmid, d->tm_w2[l], f2, st));
+    }
+    GemmArgs h0{};
+    h0.M = T; h0.N = D; h0.K = D; h0.bias = d->bh0; h0.out16 = pl->y1; h0.ld16 = D;
+    RAP_TRY(launch_gemm(EPI_F16_SILU, 128, pl->tm_hh16, d->tm_h0, h0, st));
+    GemmArgs h2{};
+    h2.M = T; h2.N = D / 2; h2.K = D; h2.bias = d->bh2; h2.out16 = pl->y2; h2.ld16 = D / 2;
+    RAP_TRY(launch_gemm(EPI_F16_SILU, 128, pl->tm_y1, d->tm_h2, h2, st));
+    return RAP_OK;
+}
+
+}  // namespace
+
+extern "C" int rap_dit_forward(rap_plan_t* pl, const float* x, const float* timesteps, float* velocity, float* features, void* stream) {
+    RAP_REQUIRE(pl && x && timesteps && velocity, "rap_dit_forward: NULL argument");
+    RAP_REQUIRE(pl->condition_set, "rap_dit_forward: call rap_plan_set_condition first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RAP_CUDA(cudaMemcpyAsync(pl->tbuf, timesteps, sizeof(float) * pl->B, cudaMemcpyDeviceToDevice, st));
+    RAP_TRY(ada_table(pl, pl->B, st));
+    RAP_TRY(dit_body(pl, x, 0, true, st));
+    RAP_TRY(launch_head_final(pl->y2, pl->dit->wh4, pl->T, velocity, nullptr, 0.f, 0.f, nullptr, nullptr, st));
+    if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->h, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
+    return RAP_OK;
+}
+
+extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps, int rigidity_forcing, float* end_traj, float* traj,
+                                float* x_final, float* features, void* stream) {
+    RAP_REQUIRE(pl && x_1, "rap_sample_euler: NULL argument");
+    RAP_REQUIRE(pl->condition_set, "rap_sample_euler: call rap_plan_set_condition first");
+    RAP_REQUIRE(num_steps >= 1 && num_steps <= pl->n_cap, "rap_sample_euler: num_steps=%d outside [1,%d] (max_timesteps of the plan)", num_steps, pl->n_cap);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t row = (size_t)pl->T * 3;
+    sampler_timesteps_kernel<<<1, 64, 0, st>>>(pl->tbuf, num_steps);
+    RAP_CUDA(cudaGetLastError());
+    note_launch(1);
+    RAP_TRY(ada_table(pl, num_steps, st));
+    RAP_CUDA(cudaMemcpyAsync(pl->x_t, x_1, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));   // x_t = x_1.clone()
+    const double dt = 1.0 / (double)num_steps;
+    for (int step = 0; step < num_steps; ++step) {
+        const double t = 1.0 - step * dt;
+        RAP_TRY(dit_body(pl, pl->x_t, step, false, st));
+        float* x0hat = end_traj ? end_traj + step * row : reinterpret_cast<float*>(pl->a_x);   // scratch when not recorded (a_x is rebuilt next step)
+        float* xt_out = (traj && !rigidity_forcing) ? traj + step * row : nullptr;
+        RAP_TRY(launch_head_final(pl->y2, pl->dit->wh4, pl->T, nullptr, pl->x_t, (float)t, (float)dt, x0hat, xt_out, st));
+        if (rigidity_forcing) {
+            // x_t = rigid(x0_hat) * (1 - t + dt) + x_1 * (t - dt)      (sampler.py:59-60)
+            RAP_TRY(launch_procrustes(pl->cond, x0hat, pl->cu_part, nullptr, pl->VP, nullptr, nullptr, pl->x_t, traj ? traj + step * row : nullptr,
+                                      x_1, (float)(1.0 - t + dt), (float)(t - dt), st));
+        }
+    }
+    if (x_final) RAP_CUDA(cudaMemcpyAsync(x_final, pl->x_t, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));
+    if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->h, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
+    return RAP_OK;
+}
+
+// ======================================================================================= procrustes
+extern "C" int rap_procrustes_fit(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
+                                  float* rotations, float* translations, void* stream) {
+    RAP_REQUIRE(source && target && cu_part && rotations && translations && n_parts >= 0, "rap_procrustes_fit: bad argument");
+    return launch_procrustes(source, target, cu_part, slot, n_parts, rotations, translations, nullptr, nullptr, nullptr, 0.f, 0.f,
+                             static_cast<cudaStream_t>(stream));
+}
+extern "C" int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_part, int n_parts, float* out,
+                                       const float* mix, float w_rigid, float w_mix, void* stream) {
+    RAP_REQUIRE(prediction && condition && cu_part && out && n_parts >= 0, "rap_procrustes_rigidify: bad argument");
+    return launch_procrustes(condition, prediction, cu_part, nullptr, n_parts, nullptr, nullptr, out, nullptr, mix, w_rigid, w_mix,
+                             static_cast<cudaStream_t>(stream));
+}
+extern "C" int rap_plan_fit(rap_plan_t* pl, const float* source, const float* target, float* rotations, float* translations, void* stream) {
+    RAP_REQUIRE(pl, "rap_plan_fit: NULL plan");
+    return rap_procrustes_fit(source, target, pl->cu_part, pl->slot, pl->VP, rotations, translations, stream);
+}
+extern "C" int rap_plan_rigidify(rap_plan_t* pl, const float* prediction, const float* condition, float* out, void* stream) {
+    RAP_REQUIRE(pl, "rap_plan_rigidify: NULL plan");
+    return rap_procrustes_rigidify(prediction, condition, pl->cu_part, pl->VP, out, nullptr, 1.0f, 0.0f, stream);
+}
+
+// ======================================================================================= micro entry points
+extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A, const void* W, const float* bias, const float* addend,
+                             float* out32, void* out16, const float* gamma, void* stream) {
+    CUtensorMap ta, tb;
+    RAP_TRY(make_tmap_f16_sw128(&ta, A, M, K, K, 128));
+    RAP_TRY(make_tmap_f16_sw128(&tb, W, N, K, K, bn));
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
+    g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N;
+    return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, void* stream) {
+    RAP_REQUIRE(heads == HEADS, "rap_test_fmha: heads must be 8");
+    std::vector<int> cu(cu_host, cu_host + n_segments + 1);
+    std::vector<int4> tiles;
+    build_tiles(cu, tiles);
+    int4* dt = nullptr;
+    RAP_CUDA(cudaMalloc(&dt, 16 * tiles.size()));
+    RAP_CUDA(cudaMemcpy(dt, tiles.data(), 16 * tiles.size(), cudaMemcpyHostToDevice));
+    CUtensorMap tm;
+    int rc = make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128);
+    if (!rc) {
+        FmhaArgs f{};
+        f.tiles = dt; f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f;
+        rc = launch_fmha(tm, f, (int)tiles.size(), heads, static_cast<cudaStream_t>(stream));
+    }
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaFree(dt);
+    return rc;
+}

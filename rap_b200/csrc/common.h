@@ -1,0 +1,48 @@
+// Host-side plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace rap {
+
+// errno-style negative return codes of the C ABI (include/rap_b200.h)
+enum : int { RAP_OK = 0, RAP_EINVAL = -22, RAP_ENOMEM = -12, RAP_ECUDA = -5, RAP_ENODEV = -19, RAP_ESTATE = -1 };
+
+void set_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define RAP_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::rap::fail(::rap::RAP_ECUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,      \
+                               cudaGetErrorString(_e));                                             \
+    } while (0)
+
+#define RAP_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) return ::rap::fail(::rap::RAP_EINVAL, __VA_ARGS__);                            \
+    } while (0)
+
+#define RAP_TRY(expr)                                                                               \
+    do {                                                                                            \
+        int _rc = (expr);                                                                           \
+        if (_rc != 0) return _rc;                                                                   \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// 2D fp16 row-major tensor map with a (box_rows x 64 cols) box and 128-byte swizzle.
+int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                        uint32_t box_rows);
+
+int num_sms();
+void note_launch(int n = 1);   // counts kernels launched by this library (rap_launch_count)
+
+}  // namespace rap

@@ -1,0 +1,241 @@
+// HBM-bound kernels around the tensor-core path: positional encoding, LayerNorm+modulation,
+// AdaLN conditioning MLP, head tail + Euler update, weight packing.  All fp32 math, fp16 only as
+// the GEMM operand format.
+#include "kernels.cuh"
+
+namespace rap {
+namespace {
+
+constexpr int D = 512;   // embed_dim (the hot path is specialised for the rap_* family: d=512, 8 heads x 64)
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// posenc element e of a 3-vector: [x(3), sin(2^0 x)(3), cos(2^0 x)(3), ..., cos(2^9 x)(3)]  (embedding.py:37-49)
+__device__ __forceinline__ float posenc3(const float* x, int e) {
+    if (e < 3) return x[e];
+    const int k = (e - 3) / 6, r = (e - 3) % 6;
+    const float a = x[r % 3] * (float)(1 << k);
+    return r < 3 ? sinf(a) : cosf(a);
+}
+__device__ __forceinline__ float posenc1(float s, int e) {   // 1-D input: [s, sin(2^0 s), cos(2^0 s), ...]
+    if (e == 0) return s;
+    const int k = (e - 1) / 2;
+    const float a = s * (float)(1 << k);
+    return ((e - 1) & 1) ? cosf(a) : sinf(a);
+}
+
+__global__ void posenc_static_kernel(const float* __restrict__ cond, const float* __restrict__ scales, const int* __restrict__ scene_of_tok,
+                                     const float* __restrict__ feats, int F, __half* __restrict__ out, int T) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = idx >> 7, e = idx & 127;
+    if (row >= T) return;
+    float v = 0.f;
+    if (e < 63) {
+        const float x[3] = {cond[row * 3], cond[row * 3 + 1], cond[row * 3 + 2]};
+        v = posenc3(x, e);
+    } else if (e < 84) {
+        v = posenc1(scales[scene_of_tok[row]], e - 63);
+    } else if (e < 84 + F) {
+        v = feats[(size_t)row * F + (e - 84)];
+    }
+    out[(size_t)row * 128 + e] = __float2half_rn(v);
+}
+
+__global__ void posenc_x_kernel(const float* __restrict__ xin, __half* __restrict__ out, int T) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = idx >> 6, e = idx & 63;
+    if (row >= T) return;
+    float v = 0.f;
+    if (e < 63) {
+        const float x[3] = {xin[row * 3], xin[row * 3 + 1], xin[row * 3 + 2]};
+        v = posenc3(x, e);
+    }
+    out[(size_t)row * 64 + e] = __float2half_rn(v);
+}
+
+// One warp per row of 512: two-pass mean/variance in registers (biased variance, eps 1e-5 like nn.LayerNorm).
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ h, __half* __restrict__ out, int T, const float* __restrict__ mul,
+                   const float* __restrict__ add, int row_stride, const int* __restrict__ row_of_tok, float one_plus) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= T) return;
+    const float4* src = reinterpret_cast<const float4*>(h + (size_t)row * D);
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = src[lane + 32 * k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        q += a * a + b * b + c * c + d * d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / D) + 1e-5f);
+    const size_t sel = row_of_tok ? (size_t)row_of_tok[row] * row_stride : 0;
+    const float4* m4 = reinterpret_cast<const float4*>(mul + sel);
+    const float4* a4 = reinterpret_cast<const float4*>(add + sel);
+    uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * D);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 m = m4[lane + 32 * k], a = a4[lane + 32 * k];
+        const float y0 = (v[k].x - mean) * rstd * (one_plus + m.x) + a.x;
+        const float y1 = (v[k].y - mean) * rstd * (one_plus + m.y) + a.y;
+        const float y2 = (v[k].z - mean) * rstd * (one_plus + m.z) + a.z;
+        const float y3 = (v[k].w - mean) * rstd * (one_plus + m.w) + a.w;
+        __half2 p0 = __floats2half2_rn(y0, y1), p1 = __floats2half2_rn(y2, y3);
+        dst[lane + 32 * k] = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    }
+}
+
+// diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_k) | sin(t f_k)], f_k = 1e4^(-k/128)
+__global__ void timestep_sincos_kernel(const float* __restrict__ t, float* __restrict__ out, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 256) return;
+    const int i = idx >> 8, e = idx & 255, k = e & 127;
+    const float f = expf(-9.210340371976184f * (float)k / 128.0f);
+    const float a = t[i] * f;
+    out[idx] = e < 128 ? cosf(a) : sinf(a);
+}
+
+// Batched small-M linear: one warp per output feature, weights held in registers, loop over the n inputs.
+template <int K>
+__global__ void __launch_bounds__(256)
+ada_linear_kernel(const __half* __restrict__ W, const float* __restrict__ b, const float* __restrict__ in, int in_has_m,
+                  float* __restrict__ out, int n, int M, int O, int silu_out) {
+    const int m = blockIdx.y, o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= O) return;
+    constexpr int PER = K / 32;
+    float w[PER];
+    const __half* wr = W + ((size_t)m * O + o) * K;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) w[i] = __half2float(wr[lane + 32 * i]);
+    const float bias = b[(size_t)m * O + o];
+    for (int i = 0; i < n; ++i) {
+        const float* x = in + (in_has_m ? ((size_t)i * M + m) * K : (size_t)i * K);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) acc = fmaf(w[j], x[lane + 32 * j], acc);
+#pragma unroll
+        for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+            acc += bias;
+            out[((size_t)i * M + m) * O + o] = silu_out ? silu_f(acc) : acc;
+        }
+    }
+}
+
+// Warp per token: v = y2 . W4^T (3 outputs), then the Euler update of sampler.py:88-90.
+__global__ void __launch_bounds__(256)
+head_final_kernel(const __half* __restrict__ y2, const float* __restrict__ W4, int T, float* __restrict__ v_out,
+                  float* __restrict__ x_t, float t, float dt, float* __restrict__ x0hat_out, float* __restrict__ xt_traj) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= T) return;
+    const uint4 raw = reinterpret_cast<const uint4*>(y2 + (size_t)row * 256)[lane];
+    const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(hp[i]); y[2 * i] = f.x; y[2 * i + 1] = f.y; }
+    float acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 w0 = reinterpret_cast<const float4*>(W4 + c * 256)[lane * 2];
+        const float4 w1 = reinterpret_cast<const float4*>(W4 + c * 256)[lane * 2 + 1];
+        acc[c] = y[0] * w0.x + y[1] * w0.y + y[2] * w0.z + y[3] * w0.w + y[4] * w1.x + y[5] * w1.y + y[6] * w1.z + y[7] * w1.w;
+#pragma unroll
+        for (int s = 16; s; s >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], s);
+    }
+    if (lane < 3) {
+        const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+        const size_t i = (size_t)row * 3 + lane;
+        if (v_out) v_out[i] = v;
+        if (x_t) {
+            const float x = x_t[i];
+            const float x0 = x - v * t;          // x_0_hat = x_t - v * t
+            const float xn = x - dt * v;         // x_t <- x_t - dt * v
+            if (x0hat_out) x0hat_out[i] = x0;
+            x_t[i] = xn;
+            if (xt_traj) xt_traj[i] = xn;
+        }
+    }
+}
+
+template <typename OutT>
+__global__ void pack_kernel(const float* __restrict__ src, OutT* __restrict__ dst, PackSpec s) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.rows * s.cols) return;
+    const int r = idx / s.cols, c = idx % s.cols;
+    int sr = r;
+    if (s.row_mode == 1) {
+        const int nt = r / 256, wi = r % 256;
+        sr = wi < 128 ? nt * 128 + wi : s.rows / 2 + nt * 128 + (wi - 128);
+    }
+    float v = 0.f;
+    int base = 0;
+    for (int k = 0; k < s.n_ranges; ++k) {
+        if (c >= base && c < base + s.range_len[k]) v = src[(size_t)sr * s.src_ld + s.range_start[k] + (c - base)];
+        base += s.range_len[k];
+    }
+    dst[idx] = OutT(v);
+}
+
+}  // namespace
+
+int launch_posenc_static(const float* cond, const float* scales, const int* scene_of_tok, const float* feats, int F,
+                         __half* out, int T, cudaStream_t st) {
+    RAP_REQUIRE(F >= 0 && F <= 44, "posenc_static: local_feat_dim %d does not fit the 128-wide operand", F);
+    posenc_static_kernel<<<ceil_div(T * 128, 256), 256, 0, st>>>(cond, scales, scene_of_tok, feats, F, out, T);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_posenc_x(const float* x, __half* out, int T, cudaStream_t st) {
+    posenc_x_kernel<<<ceil_div(T * 64, 256), 256, 0, st>>>(x, out, T);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_ln_modulate(const float* h, __half* out, int T, const float* mul, const float* add, int row_stride,
+                       const int* row_of_tok, float one_plus, cudaStream_t st) {
+    ln_modulate_kernel<<<ceil_div(T, 8), 256, 0, st>>>(h, out, T, mul, add, row_stride, row_of_tok, one_plus);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_timestep_sincos(const float* t, float* out, int n, cudaStream_t st) {
+    timestep_sincos_kernel<<<ceil_div(n * 256, 256), 256, 0, st>>>(t, out, n);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_ada_linear(const __half* W, const float* b, const float* in, int in_has_m, float* out, int n, int M, int O, int K,
+                      int silu_out, cudaStream_t st) {
+    dim3 grid(ceil_div(O, 8), M);
+    if (K == 256) ada_linear_kernel<256><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
+    else if (K == 512) ada_linear_kernel<512><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
+    else return fail(RAP_EINVAL, "ada_linear: unsupported K=%d", K);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_head_final(const __half* y2, const float* W4, int T, float* v_out, float* x_t, float t, float dt,
+                      float* x0hat_out, float* xt_traj, cudaStream_t st) {
+    head_final_kernel<<<ceil_div(T, 8), 256, 0, st>>>(y2, W4, T, v_out, x_t, t, dt, x0hat_out, xt_traj);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+int launch_pack(const float* src, void* dst, int dst_is_half, const PackSpec& spec, cudaStream_t st) {
+    const int n = spec.rows * spec.cols;
+    if (dst_is_half) pack_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), spec);
+    else pack_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(src, static_cast<float*>(dst), spec);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+
+}  // namespace rap

@@ -1,0 +1,17 @@
+// Varlen FMHA launcher (see fmha.cu).
+#pragma once
+#include "common.h"
+
+namespace rap {
+
+struct FmhaArgs {
+    const int4* tiles;   // device: {q_row0, seg_start, seg_end, 0} per 128-row query tile
+    __half* out;         // [T, d_model] fp16, head h at columns [64h, 64h+64)
+    int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
+    float scale_log2;    // log2(e) / sqrt(head_dim)
+};
+
+// tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_tiles, int heads, cudaStream_t st);
+
+}  // namespace rap

@@ -1,0 +1,32 @@
+// Persistent warp-specialised tcgen05 GEMM for the DiT projections:
+//     C[M,N] = A[M,K] (fp16, K contiguous) x W[N,K]^T (fp16, K contiguous), fp32 accumulate in TMEM,
+// with the DiT-specific epilogues fused (qk-RMSnorm, GEGLU, bias+residual, bias+SiLU).
+// One CTA per SM; warp 0 = TMA producer, warp 1 = UMMA issuer (+TMEM owner), warps 2..5 = epilogue.
+// Accumulators are double-buffered in TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's MMAs.
+#pragma once
+#include "common.h"
+
+namespace rap {
+
+enum GemmEpi : int {
+    EPI_F32 = 0,     // out32 = acc (+bias[col]) (+addend[row,col]) (+table[sel[row]][col]); optional fp16 shadow
+    EPI_F16_SILU,    // out16 = silu(acc + bias[col])
+    EPI_QKV,         // per-head RMS norm * gamma * sqrt(hd) on q,k; v passthrough; out16 [M,N]
+    EPI_GEGLU,       // tile cols [0,BN/2)=h, [BN/2,BN)=g (weights pre-interleaved); out16[M,N/2] = h*gelu(g)
+};
+
+struct GemmArgs {
+    int M, N, K;
+    const float* bias;        // [N] (packed order) or null
+    const float* addend;      // [M, ld32] or null (may alias out32)
+    float* out32;             // [M, ld32]
+    __half* out16;            // [M, ld16] (shadow for EPI_F32, main output otherwise) or null
+    int ld32, ld16;
+    const float* table;       // [2, N] row-select table (anchor embedding) or null
+    const unsigned char* sel; // [M] row selector for `table`
+    const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
+};
+
+int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t st);
+
+}  // namespace rap

@@ -1,0 +1,206 @@
+"""Python owners of the C handles: packed weights (`DiTHandle`), batch plans (`Plan`) and the
+high-level `register_batch` call that bench.py times end to end.
+
+Host side only prepares layouts and enqueues the C-ABI calls on torch's current CUDA stream; the
+math runs in librap_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rap_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class DiTHandle:
+    """Packed PointCloudDiT weights on the current device."""
+
+    def __init__(self, embed_dim: int, num_layers: int, num_heads: int, local_feat_dim: int):
+        h = C.c_void_p()
+        check(lib.rap_dit_create(C.byref(h), embed_dim, num_layers, num_heads, local_feat_dim), "rap_dit_create")
+        self._h = h
+        self.num_layers, self.embed_dim = num_layers, embed_dim
+
+    def keys(self) -> list[tuple[str, int]]:
+        out = []
+        for i in range(lib.rap_dit_num_keys(self._h)):
+            n = C.c_int64()
+            out.append((lib.rap_dit_key(self._h, i, C.byref(n)).decode(), n.value))
+        return out
+
+    def load_state_dict(self, sd: dict[str, torch.Tensor]) -> None:
+        """Strict: every reference key must be present with the reference shape, nothing extra."""
+        expected = dict(self.keys())
+        missing, unexpected = sorted(set(expected) - set(sd)), sorted(set(sd) - set(expected))
+        if missing or unexpected:
+            raise KeyError(f"state_dict mismatch: missing={missing[:4]}... unexpected={unexpected[:4]}...")
+        st = stream_ptr()
+        keep = []
+        for k, numel in expected.items():
+            w = _f32c(sd[k])
+            _require_cuda(w)
+            if w.numel() != numel:
+                raise ValueError(f"{k}: {tuple(sd[k].shape)} has {w.numel()} elements, expected {numel}")
+            keep.append(w)
+            check(lib.rap_dit_load_weight(self._h, k.encode(), ptr(w), w.numel(), st), f"load {k}")
+        torch.cuda.current_stream().synchronize()   # sources may be temporaries
+        check(lib.rap_dit_finalize(self._h), "rap_dit_finalize")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.rap_dit_destroy(self._h)
+            self._h = None
+
+
+def points_per_part_from_cu(cu_batch: np.ndarray, cu_part: np.ndarray) -> np.ndarray:
+    """(B, P) part sizes from the two cu_seqlens vectors (inverse of modeling.py:217-221)."""
+    B = len(cu_batch) - 1
+    lens = np.diff(cu_part)
+    scene = np.searchsorted(cu_batch, cu_part[:-1], side="right") - 1
+    P = max(1, int(np.bincount(scene, minlength=B).max()) if len(scene) else 1)
+    ppp = np.zeros((B, P), np.int32)
+    fill = np.zeros(B, np.int64)
+    for s, n in zip(scene, lens):
+        ppp[s, fill[s]] = n
+        fill[s] += 1
+    return ppp
+
+
+class Plan:
+    """Batch layout + workspace for one packed batch (fixed across flow steps)."""
+
+    def __init__(self, dit: DiTHandle, cu_seqlens_batch, points_per_part, max_timesteps: int = 64):
+        cu_b = np.asarray(cu_seqlens_batch, dtype=np.int64).ravel()
+        ppp = np.asarray(points_per_part, dtype=np.int64)
+        assert ppp.ndim == 2 and ppp.shape[0] == len(cu_b) - 1
+        self.dit = dit
+        self.B, self.P = ppp.shape
+        self.T = int(cu_b[-1])
+        h = C.c_void_p()
+        check(lib.rap_plan_create(C.byref(h), dit._h, self.B, _lib.i32_array(cu_b), _lib.i32_array(ppp.ravel()), self.P,
+                                  max_timesteps), "rap_plan_create")
+        self._h = h
+        self.VP = lib.rap_plan_valid_parts(h)
+        self.max_timesteps = max(max_timesteps, self.B)
+        self._cond_key = None
+        self._keep = None
+
+    # -- step-invariant inputs ------------------------------------------------------------------
+    def set_condition(self, cond, local_features, scales, anchor_indices) -> None:
+        key = tuple((t.data_ptr(), t._version) for t in (cond, local_features, scales, anchor_indices) if t is not None)
+        if key == self._cond_key:
+            return
+        _require_cuda(cond, local_features, scales, anchor_indices)
+        cond_, feats_, scales_ = _f32c(cond).reshape(-1, 3), (_f32c(local_features) if local_features is not None else None), _f32c(scales)
+        anchor_ = anchor_indices.detach().to(torch.uint8).contiguous()
+        if cond_.shape[0] != self.T or scales_.numel() != self.B or anchor_.numel() != self.T:
+            raise ValueError(f"condition tensors do not match the plan (T={self.T}, B={self.B})")
+        check(lib.rap_plan_set_condition(self._h, ptr(cond_), ptr(feats_), ptr(scales_), ptr(anchor_), stream_ptr()), "rap_plan_set_condition")
+        self._keep = (cond, local_features, scales, anchor_indices, cond_, feats_, scales_, anchor_)   # pointers stay valid
+        self._cond_key = key
+        self.cond = cond_
+
+    # -- compute ---------------------------------------------------------------------------------
+    def forward(self, x, timesteps, return_features: bool = False):
+        _require_cuda(x, timesteps)
+        x_, t_ = _f32c(x).reshape(-1, 3), _f32c(timesteps)
+        if x_.shape[0] != self.T or t_.numel() != self.B:
+            raise ValueError("x / timesteps do not match the plan")
+        v = torch.empty_like(x_)
+        feats = torch.empty(self.T, self.dit.embed_dim, device=x_.device, dtype=torch.float32) if return_features else None
+        check(lib.rap_dit_forward(self._h, ptr(x_), ptr(t_), ptr(v), ptr(feats), stream_ptr()), "rap_dit_forward")
+        return (v, feats) if return_features else v
+
+    def sample(self, x_1, num_steps: int, rigidity_forcing: bool, return_trajectory: bool = True, return_features: bool = False):
+        _require_cuda(x_1)
+        x1 = _f32c(x_1).reshape(-1, 3)
+        if x1.shape[0] != self.T:
+            raise ValueError("x_1 does not match the plan")
+        dev = x1.device
+        ep = torch.empty(num_steps, self.T, 3, device=dev) if return_trajectory else None
+        tr = torch.empty(num_steps, self.T, 3, device=dev) if return_trajectory else None
+        xf = torch.empty(self.T, 3, device=dev)
+        feats = torch.empty(self.T, self.dit.embed_dim, device=dev) if return_features else None
+        check(lib.rap_sample_euler(self._h, ptr(x1), int(num_steps), int(bool(rigidity_forcing)), ptr(ep), ptr(tr), ptr(xf), ptr(feats),
+                                   stream_ptr()), "rap_sample_euler")
+        return {"end_point_trajectory": ep, "trajectory": tr, "x_final": xf, "transformer_features": feats}
+
+    def fit(self, source, target):
+        _require_cuda(source, target)
+        s, t = _f32c(source).reshape(-1, 3), _f32c(target).reshape(-1, 3)
+        R = torch.zeros(self.B, self.P, 3, 3, device=s.device)
+        tr = torch.zeros(self.B, self.P, 3, device=s.device)
+        check(lib.rap_plan_fit(self._h, ptr(s), ptr(t), ptr(R), ptr(tr), stream_ptr()), "rap_plan_fit")
+        return R, tr
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.rap_plan_destroy(self._h)
+            self._h = None
+
+
+@dataclass
+class Registration:
+    points: torch.Tensor          # (T,3) final registered xyz = last un-rigidified x0_hat (modeling.py:365,372)
+    rotations: torch.Tensor       # (B,P,3,3)
+    translations: torch.Tensor    # (B,P,3)
+
+
+class Registrar:
+    """User-facing end-to-end call: host (pinned) batch in, registered xyz + per-view SE(3) out.
+
+    Mirrors what `RectifiedPointFlow.test_step` does for one batch (modeling.py:333-389): sampler over
+    `num_steps` Euler steps, prediction = last x0_hat, `fit_transformations(cond, prediction)`.
+    """
+
+    def __init__(self, state_dict: dict[str, torch.Tensor], num_layers: int, device: torch.device | str = "cuda",
+                 num_steps: int = 20, rigidity_forcing: bool = False, local_feat_dim: int = 32):
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.dit = DiTHandle(512, num_layers, 8, local_feat_dim)
+        self.dit.load_state_dict({k: v.to(self.device) for k, v in state_dict.items()})
+        self.num_steps, self.rigidity_forcing = num_steps, rigidity_forcing
+        self._plans: dict[bytes, Plan] = {}
+
+    def plan_for(self, cu_seqlens_batch: torch.Tensor, points_per_part: torch.Tensor) -> Plan:
+        key = cu_seqlens_batch.cpu().numpy().tobytes() + b"|" + points_per_part.cpu().numpy().tobytes()
+        p = self._plans.get(key)
+        if p is None:
+            if len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            p = self._plans[key] = Plan(self.dit, cu_seqlens_batch.cpu().numpy(), points_per_part.cpu().numpy(), max(64, self.num_steps))
+        return p
+
+    def register_device(self, plan: Plan, cond, feats, scales, anchor, x_1) -> Registration:
+        plan.set_condition(cond, feats, scales, anchor)
+        out = plan.sample(x_1, self.num_steps, self.rigidity_forcing, return_trajectory=True)
+        pred = out["end_point_trajectory"][-1]
+        R, t = plan.fit(plan.cond, pred)
+        return Registration(pred, R, t)
+
+    def register_host(self, batch) -> Registration:
+        """`batch` holds HOST tensors (ideally pinned): H2D of the inputs, compute, D2H of xyz + poses."""
+        plan = self.plan_for(batch.cu_seqlens_batch, batch.points_per_part)
+        dev = self.device
+        cond, feats, scales = (batch.cond.to(dev, non_blocking=True), batch.features.to(dev, non_blocking=True),
+                               batch.scales.to(dev, non_blocking=True))
+        anchor, x_1 = batch.anchor_indices.to(dev, non_blocking=True), batch.x_1.to(dev, non_blocking=True)
+        r = self.register_device(plan, cond, feats, scales, anchor, x_1)
+        out = Registration(r.points.to("cpu", non_blocking=True), r.rotations.to("cpu", non_blocking=True),
+                           r.translations.to("cpu", non_blocking=True))
+        torch.cuda.current_stream().synchronize()
+        return out

@@ -1,0 +1,154 @@
+"""`rectified_point_flow.flow_model.PointCloudDiT` on the sm_100a kernels.
+
+An `nn.Module` whose `state_dict()` has exactly the reference's keys and shapes (SURVEY.md 8(a) W0;
+reference flow_model/point_cloud_dit.py:82-117, layer.py:70-89, norm.py:47-58), so
+`load_checkpoint_for_module(model, ckpt)` and Hydra's `_target_` instantiation work unchanged.
+The parameters are only a container: `forward` packs them into the C library (`rap_dit_load_weight`)
+and runs the CUDA path; there is no PyTorch implementation of the math in this package.
+"""
+from __future__ import annotations
+
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ...engine import DiTHandle, Plan, points_per_part_from_cu
+
+
+class _Params(nn.Module):
+    """Parameter container: holds sub-modules / parameters under the reference's attribute names."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("container module; the math runs in librap_b200.so")
+
+
+def _linear(i: int, o: int, bias: bool = True) -> nn.Linear:
+    return nn.Linear(i, o, bias=bias)
+
+
+def _prenorm(dim: int, channels: int = 256) -> nn.Module:       # AdaptiveLayerNorm (norm.py:36-58)
+    m = _Params()
+    m.timestep_embedder = _Params()
+    m.timestep_embedder.linear_1 = _linear(channels, dim)
+    m.timestep_embedder.linear_2 = _linear(dim, dim)
+    m.linear = _linear(dim, 2 * dim)
+    return m
+
+
+def _rms(heads: int, head_dim: int) -> nn.Module:               # MultiHeadRMSNorm (norm.py:15-33)
+    m = _Params()
+    m.gamma = nn.Parameter(torch.ones(heads, head_dim))
+    return m
+
+
+def _layer(dim: int, heads: int) -> nn.Module:                  # DiTLayer (layer.py:15-96)
+    m = _Params()
+    hd = dim // heads
+    for blk in ("self", "global"):
+        setattr(m, f"{blk}_prenorm", _prenorm(dim))
+        setattr(m, f"{blk}_qkv_proj", _linear(dim, 3 * dim, bias=False))
+        setattr(m, f"{blk}_out_proj", _linear(dim, dim))
+        setattr(m, f"{blk}_q_norm", _rms(heads, hd))
+        setattr(m, f"{blk}_k_norm", _rms(heads, hd))
+    m.ff_norm = nn.LayerNorm(dim)
+    m.ff = _Params()                                            # diffusers FeedForward(dim, activation_fn="geglu")
+    geglu = _Params()
+    geglu.proj = _linear(dim, 8 * dim)
+    m.ff.net = nn.ModuleList([geglu, nn.Identity(), _linear(4 * dim, dim)])
+    return m
+
+
+class PointCloudDiT(nn.Module):
+    """Same constructor and forward signature as the reference class (point_cloud_dit.py:19-36,141-153)."""
+
+    def __init__(self, in_dim: int, out_dim: int, embed_dim: int, num_layers: int, num_heads: int, dropout_rate: float = 0.0,
+                 softcap: float = 0.0, qk_norm: bool = True, attn_dtype: str = "float16", final_mlp_act: type = nn.SiLU,
+                 max_points_per_part: int = 500, max_points_per_batch: int = 40000, scale_emb_on: bool = True,
+                 local_feat_concat_on: bool = True, local_feat_dim: int = 0):
+        super().__init__()
+        unsupported = []
+        if in_dim != 0: unsupported.append("in_dim != 0 (encoder latents)")
+        if out_dim != 3: unsupported.append("out_dim != 3")
+        if embed_dim != 512 or num_heads != 8: unsupported.append("embed_dim/num_heads other than 512/8")
+        if dropout_rate != 0.0: unsupported.append("dropout")
+        if softcap != 0.0: unsupported.append("softcap")
+        if not qk_norm: unsupported.append("qk_norm=False")
+        if final_mlp_act is not nn.SiLU: unsupported.append("final_mlp_act other than SiLU")
+        if not scale_emb_on or not local_feat_concat_on: unsupported.append("scale_emb_on/local_feat_concat_on=False")
+        if attn_dtype not in ("float16", "fp16"): unsupported.append(f"attn_dtype={attn_dtype} (kernels compute fp16 operands / fp32 accumulate)")
+        if unsupported:
+            raise NotImplementedError("rap_b200 PointCloudDiT is specialised for the released rap_10/12/16 configs; unsupported: "
+                                      + ", ".join(unsupported))
+        self.in_dim, self.out_dim, self.embed_dim, self.num_layers, self.num_heads = in_dim, out_dim, embed_dim, num_layers, num_heads
+        self.dropout_rate, self.max_points_per_part, self.max_points_per_batch = dropout_rate, max_points_per_part, max_points_per_batch
+        self.scale_emb_on, self.local_feat_concat_on, self.local_feat_dim = scale_emb_on, local_feat_concat_on, local_feat_dim
+        self.attn_dtype = torch.float16
+
+        self.anchor_part_emb = nn.Embedding(2, embed_dim)
+        self.encoding_manager = _Params()
+        self.encoding_manager.emb_proj = _linear(63 + 63 + 21 + local_feat_dim, embed_dim)
+        self.transformer_layers = nn.ModuleList([_layer(embed_dim, num_heads) for _ in range(num_layers)])
+        self.final_mlp = nn.Sequential(_linear(embed_dim, embed_dim), nn.SiLU(), _linear(embed_dim, embed_dim // 2), nn.SiLU(),
+                                       _linear(embed_dim // 2, out_dim, bias=False))
+        self._handle: DiTHandle | None = None
+        self._handle_key = None
+        self._plans: list[tuple[tuple, tuple, Plan]] = []      # (key, strong refs, plan), most recent last
+
+    # ------------------------------------------------------------------ C handles
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def handle(self) -> DiTHandle:
+        """Packed weights in the C library, refreshed whenever a parameter changed (load_state_dict, .to(), ...)."""
+        key = self._weights_key()
+        if self._handle is None or key != self._handle_key:
+            p0 = next(self.parameters())
+            if not p0.is_cuda:
+                raise RuntimeError("rap_b200 PointCloudDiT must live on a CUDA device (no CPU fallback); call .cuda() first")
+            with torch.cuda.device(p0.device):
+                h = DiTHandle(self.embed_dim, self.num_layers, self.num_heads, self.local_feat_dim)
+                h.load_state_dict(self.state_dict())
+            self._handle, self._handle_key = h, key
+            self._plans.clear()
+        return self._handle
+
+    def plan(self, cu_seqlens_batch: torch.Tensor, cu_seqlens_part: torch.Tensor, points_per_part: torch.Tensor | None = None,
+             max_timesteps: int = 64) -> Plan:
+        """Cached per batch layout.  The cache holds strong references to the key tensors so a recycled device
+        address can never alias a stale layout; the one host sync per new layout replaces the reference's
+        per-step `.tolist()` / boolean-index syncs."""
+        key = (cu_seqlens_batch.data_ptr(), cu_seqlens_batch._version, cu_seqlens_part.data_ptr(), cu_seqlens_part._version)
+        h = self.handle()
+        for k, _, p in self._plans:
+            if k == key and p.max_timesteps >= max_timesteps:
+                return p
+        cu_b = cu_seqlens_batch.detach().cpu().numpy().astype(np.int64)
+        cu_p = cu_seqlens_part.detach().cpu().numpy().astype(np.int64)
+        ppp = points_per_part.detach().cpu().numpy() if points_per_part is not None else points_per_part_from_cu(cu_b, cu_p)
+        p = Plan(h, cu_b, ppp, max_timesteps)
+        self._plans.append((key, (cu_seqlens_batch, cu_seqlens_part), p))
+        del self._plans[:-4]
+        return p
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, cond_coord: torch.Tensor, local_features: torch.Tensor | None,
+                latent_features: torch.Tensor | None, scales: torch.Tensor, anchor_indices: torch.Tensor,
+                cu_seqlens_batch: torch.Tensor, cu_seqlens_part: torch.Tensor, return_transformer_features: bool = False):
+        """x (TP,3), timesteps (B,), cond_coord (TP,3), local_features (TP,F), scales (B,), anchor_indices (TP,) bool,
+        cu_seqlens_batch (B+1,), cu_seqlens_part (VP+1,) -> velocity (TP,3) fp32, or a dict with
+        'velocity' and 'transformer_features' (TP,512) fp32.  Inference only (no autograd graph)."""
+        if latent_features is not None:
+            raise NotImplementedError("latent_features (encoder_on=True) is not part of the released inference configs")
+        if local_features is None and self.local_feat_dim:
+            raise ValueError("local_features is required (local_feat_concat_on=True)")
+        plan = self.plan(cu_seqlens_batch, cu_seqlens_part)
+        plan.set_condition(cond_coord, local_features, scales, anchor_indices)
+        if return_transformer_features:
+            v, f = plan.forward(x, timesteps.to(x.device), return_features=True)
+            return {"velocity": v, "transformer_features": f}
+        return plan.forward(x, timesteps.to(x.device))
+
+
+__all__ = ["PointCloudDiT"]

@@ -1,0 +1,157 @@
+"""Per-kernel parity on the B200 (called through the C ABI): tcgen05 GEMM epilogues, varlen FMHA, Procrustes."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rap():
+    from rap_b200 import _lib
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib
+
+
+def _sync_check(rap):
+    torch.cuda.synchronize()
+    assert rap.device_error() == 0
+
+
+def _gemm(rap, epi, bn, A, W, bias=None, addend=None, gamma=None, out16_cols=None):
+    M, K = A.shape
+    N = W.shape[0]
+    out32 = torch.zeros(M, N, device="cuda") if epi == 0 else None
+    out16 = torch.zeros(M, out16_cols or N, device="cuda", dtype=torch.float16) if (epi != 0 or out16_cols) else None
+    rap.check(rap.lib.rap_test_gemm(epi, bn, M, N, K, A.data_ptr(), W.data_ptr(), rap.ptr(bias), rap.ptr(addend), rap.ptr(out32),
+                                    rap.ptr(out16), rap.ptr(gamma), rap.stream_ptr()), "rap_test_gemm")
+    _sync_check(rap)
+    return out32, out16
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 512, 512, 128), (1024, 512, 2048, 128), (257, 512, 128, 256),
+                                       (8192, 512, 512, 128)])
+def test_gemm_f32_bias_residual(rap, M, N, K, bn):
+    g = torch.Generator("cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    add = torch.randn(M, N, device="cuda", generator=g)
+    out32, _ = _gemm(rap, 0, bn, A, W, bias, add)
+    ref = A.float() @ W.float().t() + bias + add
+    err = (out32 - ref).abs().max().item()
+    assert err < 2e-3, f"max err {err}"
+
+
+def test_gemm_silu_f16(rap):
+    g = torch.Generator("cuda").manual_seed(1)
+    A = torch.randn(500, 512, device="cuda", generator=g).half()
+    W = (torch.randn(256, 512, device="cuda", generator=g) / 22).half()
+    bias = torch.randn(256, device="cuda", generator=g)
+    _, out16 = _gemm(rap, 1, 128, A, W, bias)
+    ref = F.silu(A.float() @ W.float().t() + bias)
+    assert (out16.float() - ref).abs().max().item() < 1e-2
+
+
+def test_gemm_qkv_rmsnorm(rap):
+    g = torch.Generator("cuda").manual_seed(2)
+    M = 700
+    A = torch.randn(M, 512, device="cuda", generator=g).half()
+    W = (torch.randn(1536, 512, device="cuda", generator=g) / 22).half()
+    gamma = 1 + 0.1 * torch.randn(2, 8, 64, device="cuda", generator=g)
+    _, out16 = _gemm(rap, 2, 256, A, W, gamma=gamma)
+    qkv = (A.float() @ W.float().t()).view(M, 3, 8, 64)
+    q = F.normalize(qkv[:, 0], dim=-1) * gamma[0] * 8
+    k = F.normalize(qkv[:, 1], dim=-1) * gamma[1] * 8
+    ref = torch.stack([q, k, qkv[:, 2]], 1).reshape(M, 1536)
+    assert (out16.float() - ref).abs().max().item() < 2e-2
+
+
+def test_gemm_geglu(rap):
+    g = torch.Generator("cuda").manual_seed(3)
+    M = 333
+    A = torch.randn(M, 512, device="cuda", generator=g).half()
+    W = (torch.randn(4096, 512, device="cuda", generator=g) / 22).half()     # reference row order [h | g]
+    bias = 0.1 * torch.randn(4096, device="cuda", generator=g)
+    # pack rows the way rap_dit_load_weight does: per 256-row tile = 128 h rows then the matching 128 g rows
+    idx = torch.cat([torch.cat([torch.arange(t * 128, t * 128 + 128), 2048 + torch.arange(t * 128, t * 128 + 128)]) for t in range(16)]).cuda()
+    _, out16 = _gemm(rap, 3, 256, A, W[idx].contiguous(), bias[idx].contiguous(), out16_cols=2048)
+    hg = A.float() @ W.float().t() + bias
+    ref = hg[:, :2048] * F.gelu(hg[:, 2048:])
+    assert (out16.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048]])
+def test_fmha_varlen(rap, lens):
+    g = torch.Generator("cuda").manual_seed(sum(lens))
+    T = sum(lens)
+    qkv = torch.randn(T, 3, 8, 64, device="cuda", generator=g)
+    qkv[:, :2] = F.normalize(qkv[:, :2], dim=-1) * 8        # q,k as the RMS norm leaves them
+    qkv = qkv.half().contiguous()
+    out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array(cu), len(lens), out.data_ptr(), rap.stream_ptr()), "rap_test_fmha")
+    _sync_check(rap)
+    ref = torch.empty(T, 8, 64, device="cuda")
+    for s, e in zip(cu[:-1], cu[1:]):
+        q, k, v = (qkv[s:e, i].float().transpose(0, 1) for i in range(3))
+        ref[s:e] = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1)
+    err = (out.float().view(T, 8, 64) - ref).abs().max().item()
+    assert err < 1e-2, f"max err {err}"
+
+
+def test_procrustes_kat(rap, golden_dir):
+    from rap_b200.rectified_point_flow import procrustes
+    g = np.load(os.path.join(golden_dir, "procrustes_kat.npz"))
+    for i in range(5):
+        src, tgt = torch.from_numpy(g[f"src{i}"]).cuda(), torch.from_numpy(g[f"tgt{i}"]).cuda()
+        R, t = procrustes.solve_procrustes(src, tgt)
+        _sync_check(rap)
+        np.testing.assert_allclose(R.cpu().numpy(), g[f"R{i}"], atol=2e-5)
+        np.testing.assert_allclose(t.cpu().numpy(), g[f"t{i}"], atol=2e-5)
+
+
+def test_fit_and_rigidify_match_reference_golden(rap, golden_dir):
+    from oracle.make_golden import CASES
+    from rap_b200.rectified_point_flow import procrustes
+    from rap_b200.synth import make_batch
+    name = "ragged_b2_v3_L2_s3_rigid"
+    _, B, V, N, _, _ = CASES[name]
+    b = make_batch(B, V, N, max_parts=V + 2)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    pred = torch.from_numpy(g["end_point_trajectory"][-1]).cuda()
+    cond, ppp, cu = b.cond.cuda(), b.points_per_part.cuda(), b.cu_seqlens_batch.cuda()
+    R, t = procrustes.fit_transformations(cond, pred, ppp, cu)
+    rig = procrustes.rigidify_prediction_with_procrustes(pred, cond, ppp, cu)
+    _sync_check(rap)
+    assert R.shape == (B, V + 2, 3, 3) and t.shape == (B, V + 2, 3)
+    np.testing.assert_allclose(rig.cpu().numpy(), g["rigidified"], atol=2e-5)
+    applied = torch.einsum("nij,nj->ni", R.repeat_interleave(ppp.reshape(-1), 0).reshape(-1, 3, 3), cond) + t.repeat_interleave(ppp.reshape(-1), 0).reshape(-1, 3)
+    np.testing.assert_allclose(applied.cpu().numpy(), g["rigidified"], atol=2e-5)
+    empty = (ppp == 0)
+    assert R[empty].abs().max() == 0 and t[empty].abs().max() == 0
+    with pytest.raises(ValueError):
+        procrustes.fit_transformations(cond, pred, ppp, None)
+    # (B,N,3) fixed-batching input (utils/point_clouds.py:50-55)
+    Rb, tb = procrustes.fit_transformations(cond.view(B, -1, 3), pred.view(B, -1, 3), ppp)
+    assert torch.equal(Rb, R) and torch.equal(tb, t)
+
+
+def test_procrustes_planted_full_size(rap):
+    """Size-independent property at BASELINE sizes: a planted rigid motion of 2x4096-point views is recovered."""
+    from rap_b200.rectified_point_flow import procrustes
+    g = torch.Generator("cuda").manual_seed(5)
+    src = torch.randn(2 * 4096, 3, device="cuda", generator=g)
+    q, _ = torch.linalg.qr(torch.randn(2, 3, 3, device="cuda", generator=g))
+    q = q * torch.sign(torch.det(q))[:, None, None]
+    tt = torch.randn(2, 3, device="cuda", generator=g)
+    tgt = torch.cat([src[:4096] @ q[0].t() + tt[0], src[4096:] @ q[1].t() + tt[1]])
+    ppp = torch.tensor([[4096, 4096]], device="cuda")
+    R, t = procrustes.fit_transformations(src, tgt, ppp, torch.tensor([0, 8192], device="cuda", dtype=torch.int32))
+    _sync_check(rap)
+    assert (R[0] - q).abs().max() < 1e-5 and (t[0] - tt).abs().max() < 1e-5
