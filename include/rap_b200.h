@@ -84,11 +84,24 @@ int rap_kabsch_host(const double* H9, double* R9);
 /* Kernel launch counter (incremented by every kernel this library launches; for bench.py's gpu_launches). */
 int64_t rap_launch_count(void);
 
+/* Per-kernel-class device timing (CUDA events around every launch on the launching stream) between
+ * rap_profile_begin and rap_profile_end (host-synchronising); arrays have rap_profile_classes() entries. */
+int rap_profile_begin(void);
+int rap_profile_end(float* total_ms_per_class, int* launches_per_class);
+int rap_profile_classes(void);
+const char* rap_profile_class_name(int kernel_class);
+
 /* Micro entry points used by tests/ and profiling to exercise one kernel at a time. */
 int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
                   const float* addend, float* out32, void* out16, const float* gamma, void* stream);
 int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out_f16,
                   void* stream);
+
+int rap_test_ln_modulate(const float* h, void* out_f16, int T, const float* mul, const float* add, int row_stride,
+                         const int32_t* row_of_tok, float one_plus, void* stream);
+/* Debug/test: copy a plan-internal device buffer to `dst` (device). 0 scene_of_tok, 1 AdaLN table, 2 h, 3 h_static,
+ * 4 x16, 5 qkv, 6 attn16. */
+int rap_debug_read(rap_plan_t* plan, int which, void* dst, int64_t bytes);
 
 #ifdef __cplusplus
 }

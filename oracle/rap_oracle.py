@@ -39,7 +39,7 @@ def posenc(x: torch.Tensor, num_freqs: int = 10) -> torch.Tensor:
 
 def repeat_by_cu_seqlens(x: torch.Tensor, cu: torch.Tensor) -> torch.Tensor:
     """utils/point_clouds.py:161-183."""
-    lens = (cu[1:] - cu[:-1]).long()
+    lens = (cu[1:] - cu[:-1]).long().to(x.device)
     return x.repeat_interleave(lens, dim=0)
 
 
@@ -61,7 +61,7 @@ def timestep_sincos(t: torch.Tensor, channels: int = 256) -> torch.Tensor:
     """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) as built at
     flow_model/norm.py:50-52: [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / 128)."""
     half = channels // 2
-    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).to(t.dtype)
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half).to(t.dtype)
     a = t[:, None] * f[None]
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
 
@@ -92,8 +92,8 @@ def varlen_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu: torc
     for s, e in zip(bounds[:-1], bounds[1:]):
         if e == s:
             continue
-        a = torch.einsum("nhd,mhd->hnm", q[s:e], k[s:e]) / math.sqrt(hd)
-        out[s:e] = torch.einsum("hnm,mhd->nhd", torch.softmax(a, dim=-1), v[s:e])
+        qs, ks, vs = (t[s:e].transpose(0, 1)[None] for t in (q, k, v))               # (1,H,n,hd)
+        out[s:e] = F.scaled_dot_product_attention(qs, ks, vs, scale=1.0 / math.sqrt(hd))[0].transpose(0, 1)
     return out
 
 

@@ -49,7 +49,13 @@ PROTOTYPES = {
     "rap_plan_rigidify": (C.c_int, [_vp, _f32p, _f32p, _f32p, _vp]),
     "rap_kabsch_host": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rap_launch_count": (C.c_int64, []),
+    "rap_profile_begin": (C.c_int, []),
+    "rap_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "rap_profile_classes": (C.c_int, []),
+    "rap_profile_class_name": (C.c_char_p, [C.c_int]),
     "rap_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _f32p, _f32p, _vp, _f32p, _vp]),
+    "rap_test_ln_modulate": (C.c_int, [_f32p, _vp, C.c_int, _f32p, _f32p, C.c_int, _vp, C.c_float, _vp]),
+    "rap_debug_read": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, _vp]),
 }
 for _name, (_res, _args) in PROTOTYPES.items():
@@ -84,3 +90,19 @@ def stream_ptr() -> int:
 def i32_array(values) -> C.Array:
     vals = [int(v) for v in values]
     return (C.c_int32 * len(vals))(*vals)
+
+
+class profile:
+    """Context manager: per-kernel-class device time of everything the library launches inside the block."""
+
+    def __enter__(self):
+        check(lib.rap_profile_begin(), "rap_profile_begin")
+        self.result = {}
+        return self
+
+    def __exit__(self, *exc):
+        n = lib.rap_profile_classes()
+        ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+        check(lib.rap_profile_end(ms, cnt), "rap_profile_end")
+        self.result = {lib.rap_profile_class_name(i).decode(): {"ms": float(ms[i]), "launches": int(cnt[i])} for i in range(n) if cnt[i]}
+        return False

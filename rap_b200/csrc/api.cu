@@ -31,6 +31,25 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+struct ProfEvent { int kc; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open[KC_COUNT];
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+bool profiling_enabled() { return g_prof_on; }
+void profile_mark(int kc, cudaStream_t st, bool end) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, st);
+    if (!end) g_prof_open[kc] = e;
+    else g_prof_events.push_back({kc, g_prof_open[kc], e});
+}
+
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -312,7 +331,7 @@ struct rap_plan {
     int n_tiles_part = 0, n_tiles_batch = 0;
     char* ws = nullptr;
     // layout
-    int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr;
+    int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr, *zero_rows = nullptr;
     int4 *tiles_part = nullptr, *tiles_batch = nullptr;
     // activations
     float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
@@ -370,7 +389,7 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     const size_t Tp = (size_t)((T + 127) / 128) * 128;     // padded rows so tail tiles stay in-bounds for plain loads/stores
     size_t bytes = 0;
     auto need = [&](size_t n) { bytes = ((bytes + 255) & ~size_t(255)) + n; };
-    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(16 * tp.size()); need(16 * tb.size());
+    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(4 * (size_t)T); need(16 * tp.size()); need(16 * tb.size());
     need(4 * Tp * D); need(4 * Tp * D); need(4 * Tp * 3); need(4 * (size_t)pl->n_cap);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * 3 * D); need(2 * Tp * FF_INNER); need(2 * Tp * 128); need(2 * Tp * 64);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * (D / 2));
@@ -379,7 +398,7 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     if (cudaMalloc(&pl->ws, bytes) != cudaSuccess) { delete pl; return fail(RAP_ENOMEM, "rap_plan_create: cudaMalloc(%zu) failed", bytes); }
     cudaMemset(pl->ws, 0, bytes);
     Slab s; s.base = pl->ws; s.size = bytes;
-    pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T);
+    pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T); pl->zero_rows = s.take<int>(T);
     pl->tiles_part = s.take<int4>(tp.size()); pl->tiles_batch = s.take<int4>(tb.size());
     pl->h = s.take<float>(Tp * D); pl->h_static = s.take<float>(Tp * D); pl->x_t = s.take<float>(Tp * 3); pl->tbuf = s.take<float>(pl->n_cap);
     pl->x16 = s.take<__half>(Tp * D); pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
@@ -457,7 +476,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
     for (int l = 0; l < d->L; ++l) {
         for (int b = 0; b < 2; ++b) {
             const float* ss = pl->ada_tab + ((size_t)tab_row0 * M + (2 * l + b)) * 2 * D;
-            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, ss, ss + D, row_stride, per_scene ? pl->scene_of_tok : nullptr, 1.0f, st));
+            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, ss, ss + D, row_stride, per_scene ? pl->scene_of_tok : pl->zero_rows, 1.0f, st));
             GemmArgs q{};
             q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
@@ -468,7 +487,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
             RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_attn16, d->tm_out[b][l], o, st));
         }
-        RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, nullptr, 0.0f, st));
+        RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, pl->zero_rows, 0.0f, st));
         GemmArgs f1{};
         f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER;
         RAP_TRY(launch_gemm(EPI_GEGLU, 256, pl->tm_x16, d->tm_w1[l], f1, st));
@@ -582,4 +601,56 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     cudaFree(dt);
     return rc;
+}
+
+extern "C" int rap_test_ln_modulate(const float* h, void* out16, int T, const float* mul, const float* add, int row_stride, const int32_t* row_of_tok,
+                                    float one_plus, void* stream) {
+    return launch_ln_modulate(h, static_cast<__half*>(out16), T, mul, add, row_stride, row_of_tok, one_plus, static_cast<cudaStream_t>(stream));
+}
+// Copies plan-internal buffers out for debugging/tests: which = 0 scene_of_tok (T i32), 1 AdaLN table (n_cap*M*1024 f32), 2 h (T*512 f32),
+// 3 h_static (T*512 f32), 4 x16 (T*512 f16), 5 qkv (T*1536 f16), 6 attn16 (T*512 f16).
+extern "C" int rap_debug_read(rap_plan_t* pl, int which, void* dst, int64_t bytes) {
+    RAP_REQUIRE(pl && dst, "rap_debug_read: NULL");
+    const void* src = nullptr;
+    switch (which) {
+        case 0: src = pl->scene_of_tok; break;
+        case 1: src = pl->ada_tab; break;
+        case 2: src = pl->h; break;
+        case 3: src = pl->h_static; break;
+        case 4: src = pl->x16; break;
+        case 5: src = pl->qkv; break;
+        case 6: src = pl->attn16; break;
+        default: return fail(RAP_EINVAL, "rap_debug_read: bad selector");
+    }
+    RAP_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+    return RAP_OK;
+}
+
+// ======================================================================================= profiling
+extern "C" int rap_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = true;
+    return RAP_OK;
+}
+// Host-synchronising.  ms_out / count_out: arrays of rap_profile_classes() entries (total ms, launches) per kernel class.
+extern "C" int rap_profile_end(float* ms_out, int* count_out) {
+    RAP_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    for (int i = 0; i < KC_COUNT; ++i) { if (ms_out) ms_out[i] = 0.f; if (count_out) count_out[i] = 0; }
+    for (auto& ev : g_prof_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
+        if (ms_out) ms_out[ev.kc] += ms;
+        if (count_out) count_out[ev.kc] += 1;
+        g_prof_pool.push_back(ev.a); g_prof_pool.push_back(ev.b);
+    }
+    g_prof_events.clear();
+    return RAP_OK;
+}
+extern "C" int rap_profile_classes(void) { return KC_COUNT; }
+extern "C" const char* rap_profile_class_name(int kc) {
+    static const char* names[KC_COUNT] = {"gemm_f32_bias_residual", "gemm_f16_silu", "gemm_qkv_rmsnorm", "gemm_geglu", "fmha_varlen", "ln_modulate",
+                                          "posenc", "head_final_euler", "adaln_table", "procrustes", "weight_pack"};
+    return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "";
 }

@@ -45,4 +45,16 @@ int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint6
 int num_sms();
 void note_launch(int n = 1);   // counts kernels launched by this library (rap_launch_count)
 
+// Optional per-kernel-class timing (rap_profile_begin/_end): CUDA events recorded on the launching stream
+// around every launch of the library's kernels, so bench.py can report live per-kernel durations.
+enum KernelClass : int { KC_GEMM_F32 = 0, KC_GEMM_SILU, KC_GEMM_QKV, KC_GEMM_GEGLU, KC_FMHA, KC_LN, KC_POSENC, KC_HEAD, KC_ADA,
+                         KC_PROCRUSTES, KC_PACK, KC_COUNT };
+bool profiling_enabled();
+void profile_mark(int kc, cudaStream_t st, bool end);
+struct ProfScope {
+    int kc; cudaStream_t st; bool on;
+    ProfScope(int k, cudaStream_t s) : kc(k), st(s), on(profiling_enabled()) { if (on) profile_mark(kc, st, false); }
+    ~ProfScope() { if (on) profile_mark(kc, st, true); }
+};
+
 }  // namespace rap

@@ -3,6 +3,8 @@
 // the GEMM operand format.
 #include "kernels.cuh"
 
+namespace rap { extern __device__ unsigned int g_dev_error; }
+
 namespace rap {
 namespace {
 
@@ -56,7 +58,7 @@ __global__ void posenc_x_kernel(const float* __restrict__ xin, __half* __restric
 // One warp per row of 512: two-pass mean/variance in registers (biased variance, eps 1e-5 like nn.LayerNorm).
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ h, __half* __restrict__ out, int T, const float* __restrict__ mul,
-                   const float* __restrict__ add, int row_stride, const int* __restrict__ row_of_tok, float one_plus) {
+                   const float* __restrict__ add, int row_stride, const int* row_of_tok, float one_plus) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     const float4* src = reinterpret_cast<const float4*>(h + (size_t)row * D);
@@ -76,7 +78,9 @@ ln_modulate_kernel(const float* __restrict__ h, __half* __restrict__ out, int T,
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * (1.0f / D) + 1e-5f);
-    const size_t sel = row_of_tok ? (size_t)row_of_tok[row] * row_stride : 0;
+    // row_of_tok is never null (the uniform case passes an all-zero index vector): an earlier variant with a
+    // predicated load of the index produced wild per-lane addresses on sm_100a; the unconditional form is robust.
+    const size_t sel = (size_t)row_of_tok[row] * (size_t)row_stride;
     const float4* m4 = reinterpret_cast<const float4*>(mul + sel);
     const float4* a4 = reinterpret_cast<const float4*>(add + sel);
     uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * D);
@@ -188,12 +192,14 @@ __global__ void pack_kernel(const float* __restrict__ src, OutT* __restrict__ ds
 int launch_posenc_static(const float* cond, const float* scales, const int* scene_of_tok, const float* feats, int F,
                          __half* out, int T, cudaStream_t st) {
     RAP_REQUIRE(F >= 0 && F <= 44, "posenc_static: local_feat_dim %d does not fit the 128-wide operand", F);
+    ProfScope _ps(KC_POSENC, st);
     posenc_static_kernel<<<ceil_div(T * 128, 256), 256, 0, st>>>(cond, scales, scene_of_tok, feats, F, out, T);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;
 }
 int launch_posenc_x(const float* x, __half* out, int T, cudaStream_t st) {
+    ProfScope _ps(KC_POSENC, st);
     posenc_x_kernel<<<ceil_div(T * 64, 256), 256, 0, st>>>(x, out, T);
     RAP_CUDA(cudaGetLastError());
     note_launch();
@@ -201,12 +207,14 @@ int launch_posenc_x(const float* x, __half* out, int T, cudaStream_t st) {
 }
 int launch_ln_modulate(const float* h, __half* out, int T, const float* mul, const float* add, int row_stride,
                        const int* row_of_tok, float one_plus, cudaStream_t st) {
+    ProfScope _ps(KC_LN, st);
     ln_modulate_kernel<<<ceil_div(T, 8), 256, 0, st>>>(h, out, T, mul, add, row_stride, row_of_tok, one_plus);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;
 }
 int launch_timestep_sincos(const float* t, float* out, int n, cudaStream_t st) {
+    ProfScope _ps(KC_ADA, st);
     timestep_sincos_kernel<<<ceil_div(n * 256, 256), 256, 0, st>>>(t, out, n);
     RAP_CUDA(cudaGetLastError());
     note_launch();
@@ -214,6 +222,7 @@ int launch_timestep_sincos(const float* t, float* out, int n, cudaStream_t st) {
 }
 int launch_ada_linear(const __half* W, const float* b, const float* in, int in_has_m, float* out, int n, int M, int O, int K,
                       int silu_out, cudaStream_t st) {
+    ProfScope _ps(KC_ADA, st);
     dim3 grid(ceil_div(O, 8), M);
     if (K == 256) ada_linear_kernel<256><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
     else if (K == 512) ada_linear_kernel<512><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
@@ -224,12 +233,14 @@ int launch_ada_linear(const __half* W, const float* b, const float* in, int in_h
 }
 int launch_head_final(const __half* y2, const float* W4, int T, float* v_out, float* x_t, float t, float dt,
                       float* x0hat_out, float* xt_traj, cudaStream_t st) {
+    ProfScope _ps(KC_HEAD, st);
     head_final_kernel<<<ceil_div(T, 8), 256, 0, st>>>(y2, W4, T, v_out, x_t, t, dt, x0hat_out, xt_traj);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;
 }
 int launch_pack(const float* src, void* dst, int dst_is_half, const PackSpec& spec, cudaStream_t st) {
+    ProfScope _ps(KC_PACK, st);
     const int n = spec.rows * spec.cols;
     if (dst_is_half) pack_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), spec);
     else pack_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(src, static_cast<float*>(dst), spec);

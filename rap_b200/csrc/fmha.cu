@@ -218,6 +218,7 @@ int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int h
         RAP_CUDA(cudaFuncSetAttribute(fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
+    ProfScope _ps(KC_FMHA, st);
     fmha_kernel<<<dim3(n_tiles, heads), kThreads, SMEM_BYTES, st>>>(tm_qkv, a);
     RAP_CUDA(cudaGetLastError());
     note_launch();

@@ -245,6 +245,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
     }
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    ProfScope _ps(EPI == EPI_F32 ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
     gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, a);
     RAP_CUDA(cudaGetLastError());
     note_launch();

@@ -12,7 +12,7 @@ int launch_posenc_static(const float* cond, const float* scales, const int* scen
 int launch_posenc_x(const float* x, __half* out, int T, cudaStream_t st);
 
 // ---- LayerNorm (+AdaLN modulation) -> fp16 GEMM operand (flow_model/norm.py:76, layer.py:163) ---
-// out = LN(h) * (one_plus + mul[c]) + add[c]; mul/add rows selected per token via row_of_tok (null -> row 0).
+// out = LN(h) * (one_plus + mul[c]) + add[c]; mul/add rows selected per token via row_of_tok (never null).
 int launch_ln_modulate(const float* h, __half* out, int T, const float* mul, const float* add, int row_stride,
                        const int* row_of_tok, float one_plus, cudaStream_t st);
 

@@ -172,6 +172,7 @@ int launch_procrustes(const float* src, const float* tgt, const int* cu_part, co
                       float* R_out, float* t_out, float* apply_out, float* apply_out2, const float* mix,
                       float w_rigid, float w_mix, cudaStream_t st) {
     if (n_parts <= 0) return RAP_OK;
+    ProfScope _ps(KC_PROCRUSTES, st);
     procrustes_kernel<<<n_parts, kThreads, 0, st>>>(src, tgt, cu_part, slot, R_out, t_out, apply_out, apply_out2, mix, w_rigid, w_mix);
     RAP_CUDA(cudaGetLastError());
     note_launch();

@@ -1,0 +1,140 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rap_b200.h declares, the host-side
+Kabsch solve matches the oracle, layout helpers, module surface / drop-in aliasing, and loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "rap_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rap_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rap_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/rap_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert _lib.lib.rap_version() >= 100
+
+
+def test_kabsch_host_matches_oracle_incl_reflection_and_rank_deficiency():
+    from oracle import rap_oracle as orc
+    from rap_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    for n, reflect in [(50, False), (50, True), (3, False), (1000, False)]:
+        src = torch.randn(n, 3, generator=g, dtype=torch.float64)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+        if (torch.det(q) < 0) != reflect:
+            q[:, 0] *= -1
+        tgt = src @ q.t() + 0.01 * torch.randn(n, 3, generator=g, dtype=torch.float64)
+        H = ((src - src.mean(0)).t() @ (tgt - tgt.mean(0))).contiguous()
+        Hc, Rc = (C.c_double * 9)(*H.flatten().tolist()), (C.c_double * 9)()
+        assert _lib.lib.rap_kabsch_host(Hc, Rc) == 0
+        R = torch.tensor(list(Rc), dtype=torch.float64).view(3, 3)
+        Ro, _ = orc.solve_procrustes(src, tgt)
+        assert abs(float(torch.det(R)) - 1) < 1e-9
+        assert (R - Ro).abs().max() < 1e-8
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rap_b200 import _lib
+    from rap_b200.rectified_point_flow import procrustes
+    from rap_b200.rectified_point_flow.flow_model import PointCloudDiT
+    h = C.c_void_p()
+    rc = _lib.lib.rap_dit_create(C.byref(h), 512, 2, 8, 32)
+    assert rc != 0 and b"no CUDA device" in _lib.lib.rap_last_error()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        procrustes.solve_procrustes(torch.zeros(4, 3), torch.zeros(4, 3))
+    m = PointCloudDiT(in_dim=0, out_dim=3, embed_dim=512, num_layers=1, num_heads=8, local_feat_dim=32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(4, 3), torch.zeros(1), torch.zeros(4, 3), torch.zeros(4, 32), None, torch.ones(1),
+          torch.zeros(4, dtype=torch.bool), torch.tensor([0, 4]), torch.tensor([0, 4]))
+
+
+def test_state_dict_surface_matches_reference_keys():
+    from rap_b200.rectified_point_flow.flow_model import PointCloudDiT
+    from rap_b200.synth import DiTConfig, make_state_dict, state_dict_spec
+    for L in (1, 3):
+        m = PointCloudDiT(in_dim=0, out_dim=3, embed_dim=512, num_layers=L, num_heads=8, local_feat_dim=32)
+        spec = state_dict_spec(DiTConfig(num_layers=L))
+        sd = m.state_dict()
+        assert list(sd) == [k for k, _, _ in spec]
+        assert all(tuple(sd[k].shape) == s for k, s, _ in spec)
+        missing, unexpected = m.load_state_dict(make_state_dict(DiTConfig(num_layers=L)), strict=True)
+        assert not missing and not unexpected
+    with pytest.raises(NotImplementedError):
+        PointCloudDiT(in_dim=0, out_dim=3, embed_dim=256, num_layers=1, num_heads=8)
+
+
+def test_sampler_surface_and_closure_introspection():
+    from rap_b200.rectified_point_flow import sampler
+    from rap_b200.rectified_point_flow.flow_model import PointCloudDiT
+    with pytest.raises(ValueError, match="Unknown sampler"):
+        sampler.get_sampler("rk2")
+    f = sampler.get_sampler("euler")
+    assert f.func is sampler.flow_sampler and f.args == (sampler.euler_step,)
+
+    class Harness:
+        flow_model = PointCloudDiT(in_dim=0, out_dim=3, embed_dim=512, num_layers=1, num_heads=8, local_feat_dim=32)
+
+    self = Harness()
+    cond = local_features = scales = anchor_indices = cu_seqlens_batch = cu_seqlens_part = torch.zeros(1)
+    latent_features = None
+
+    def closure(x, t):
+        return self.flow_model, cond, local_features, latent_features, scales, anchor_indices, cu_seqlens_batch, cu_seqlens_part
+
+    model, ctx, cells = sampler._fused_context(closure)
+    assert model is self.flow_model and ctx["cond"] is cond and "self" in cells
+    assert sampler._fused_context(lambda x, t: x) is None          # opaque callables take the per-step route
+
+
+def test_install_aliases_reference_module_names():
+    import rap_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "rectified_point_flow" or k.startswith("rectified_point_flow.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        rap_b200.install()
+        import rectified_point_flow.sampler as s
+        from rectified_point_flow.flow_model import PointCloudDiT
+        from rectified_point_flow.procrustes import fit_transformations
+        assert s.__name__ == "rap_b200.rectified_point_flow.sampler"
+        assert PointCloudDiT.__module__.startswith("rap_b200.") and fit_transformations.__module__.startswith("rap_b200.")
+    finally:
+        for k in [k for k in sys.modules if k == "rectified_point_flow" or k.startswith("rectified_point_flow.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_points_per_part_from_cu_roundtrip():
+    from rap_b200.engine import points_per_part_from_cu
+    ppp = np.array([[200, 136, 72, 0], [5, 0, 0, 0], [64, 64, 64, 64]])
+    cu_b = np.concatenate([[0], np.cumsum(ppp.sum(1))])
+    cu_p = np.concatenate([[0], np.cumsum(ppp[ppp > 0])])
+    out = points_per_part_from_cu(cu_b, cu_p)
+    assert out.shape == (3, 4) and (out == ppp).all()
+
+
+def test_split_parts_and_repeat_helpers():
+    from rap_b200.rectified_point_flow.utils.point_clouds import repeat_by_cu_seqlens, split_parts
+    x = torch.arange(30.).view(10, 3)
+    parts = split_parts(x, torch.tensor([[2, 0, 4], [4, 0, 0]]), torch.tensor([0, 6, 10]))
+    assert [len(p) for p in parts] == [2, 1] and parts[0][1].shape == (4, 3) and torch.equal(parts[1][0], x[6:])
+    with pytest.raises(ValueError):
+        split_parts(x, torch.tensor([[10]]))
+    r = repeat_by_cu_seqlens(torch.tensor([[1.], [2.]]), torch.tensor([0, 2, 5]))
+    assert r.flatten().tolist() == [1, 1, 2, 2, 2]

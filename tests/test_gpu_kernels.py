@@ -131,7 +131,8 @@ def test_fit_and_rigidify_match_reference_golden(rap, golden_dir):
     _sync_check(rap)
     assert R.shape == (B, V + 2, 3, 3) and t.shape == (B, V + 2, 3)
     np.testing.assert_allclose(rig.cpu().numpy(), g["rigidified"], atol=2e-5)
-    applied = torch.einsum("nij,nj->ni", R.repeat_interleave(ppp.reshape(-1), 0).reshape(-1, 3, 3), cond) + t.repeat_interleave(ppp.reshape(-1), 0).reshape(-1, 3)
+    reps = ppp.reshape(-1)
+    applied = torch.einsum("nij,nj->ni", R.reshape(-1, 3, 3).repeat_interleave(reps, 0), cond) + t.reshape(-1, 3).repeat_interleave(reps, 0)
     np.testing.assert_allclose(applied.cpu().numpy(), g["rigidified"], atol=2e-5)
     empty = (ppp == 0)
     assert R[empty].abs().max() == 0 and t[empty].abs().max() == 0
