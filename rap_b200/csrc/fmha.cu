@@ -129,16 +129,21 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                     for (int i = 0; i < 32; ++i)
                         if (c * 32 + i >= valid) sreg[c][i] = 0xff800000u;   // -inf
             }
-            float mx = -INFINITY;
+            // Row max / row sum with 8 independent accumulators: a single dependent FMNMX/FADD chain over 128 columns
+            // is latency-bound with only two softmax warps per scheduler.
+            float mxa[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sreg[c][i]));
+                for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
+            const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
             const float m_new = fmaxf(m_run, mx * sl2);
             const float alpha = ex2f(m_run - m_new);
             const bool grew = m_new > m_run;
             m_run = m_new;
-            float lsum = 0.f;
+            float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             uint32_t preg[64];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -146,9 +151,10 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 for (int i = 0; i < 32; i += 2) {
                     const float a = ex2f(fmaf(__uint_as_float(sreg[c][i]), sl2, -m_new));
                     const float b = ex2f(fmaf(__uint_as_float(sreg[c][i + 1]), sl2, -m_new));
-                    lsum += a + b;
+                    ls[(i >> 1) & 7] += a + b;
                     preg[c * 16 + i / 2] = pack_half2(a, b);
                 }
+            const float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
             l_run = l_run * alpha + lsum;
 
             if (j > 0) {

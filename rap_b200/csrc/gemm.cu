@@ -15,7 +15,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 template <int BN> struct Cfg {
@@ -27,7 +27,18 @@ template <int BN> struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/ + 4096 /*gamma*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU.  1+erf(z) through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 output grid):
+//   z>=0: 2 - poly(t) e^{-z^2},  z<0: poly(t) e^{-z^2},  t = 1/(1 + 0.3275911 |z|)   -- one rcp, one ex2, 7 FMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = x * 0.70710678118654752f, az = fabsf(z);
+    const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    const float e = pl * t * ex2f(-az * az * 1.4426950408889634f);
+    return 0.5f * x * (z >= 0.f ? 2.0f - e : e);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 template <int BN, int EPI>
@@ -54,7 +65,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -107,34 +118,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+        // ------------------------------------------------------------ epilogue: 8 warps.  TMEM lane quarter = warp % 4
+        // (hardware rule), column half = (warp - 2) / 4, so two warps share a quarter and split the tile's columns.
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int HC = BN / 2;                       // columns per warp
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
-            mbar_wait(tfull_bar(acc), acc_phase, 0x31);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
             uint32_t r[32];
 
             if constexpr (EPI == EPI_F32) {
+                // Prefetch the addend (residual / static embedding) row segment into registers BEFORE waiting for the
+                // accumulator: the loads fly under this tile's MMAs instead of serialising with the TMEM reads.
+                const int col0 = n0 + half * HC;
+                float4 ad[HC / 4];
+                if (p.addend && row_ok) {
+                    const float4* a4 = reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld32 + col0);
+#pragma unroll
+                    for (int i = 0; i < HC / 4; ++i) ad[i] = a4[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < HC / 4; ++i) ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 const float* tab = (p.table && row_ok) ? p.table + (size_t)(p.sel[row] ? 1 : 0) * p.N : nullptr;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    tmem_ld32(t_row + c * 32, r);
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < HC / 32; ++c) {
+                    tmem_ld32(t_row + half * HC + c * 32, r);
                     tmem_ld_wait();
                     if (row_ok) {
-                        const int col = n0 + c * 32;
+                        const int col = col0 + c * 32;
                         float* o = p.out32 + (size_t)row * p.ld32 + col;
-                        const float* ad = p.addend ? p.addend + (size_t)row * p.ld32 + col : nullptr;
                         uint32_t h16[16];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                            const float4 a = ad[c * 8 + i / 4];
+                            float4 v = make_float4(__uint_as_float(r[i]) + a.x, __uint_as_float(r[i + 1]) + a.y, __uint_as_float(r[i + 2]) + a.z,
+                                                   __uint_as_float(r[i + 3]) + a.w);
                             if (p.bias) { float4 b = *reinterpret_cast<const float4*>(p.bias + col + i); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-                            if (ad) { float4 a = *reinterpret_cast<const float4*>(ad + i); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
                             if (tab) { float4 t = *reinterpret_cast<const float4*>(tab + col + i); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
                             *reinterpret_cast<float4*>(o + i) = v;
                             h16[i / 2] = pack_half2(v.x, v.y);
@@ -148,12 +174,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
             } else if constexpr (EPI == EPI_F16_SILU) {
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    tmem_ld32(t_row + c * 32, r);
+                for (int c = 0; c < HC / 32; ++c) {
+                    tmem_ld32(t_row + half * HC + c * 32, r);
                     tmem_ld_wait();
                     if (row_ok) {
-                        const int col = n0 + c * 32;
+                        const int col = n0 + half * HC + c * 32;
                         uint4* o16 = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
@@ -168,8 +196,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // One 64-column head per iteration.  section 0/1 = q/k (RMS-normalised), 2 = v.
                 const int dmodel = p.N / 3;
                 uint32_t r2[32];
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
 #pragma unroll 1
-                for (int hc = 0; hc < BN / 64; ++hc) {
+                for (int hc = half * (HC / 64); hc < (half + 1) * (HC / 64); ++hc) {
                     tmem_ld32(t_row + hc * 64, r);
                     tmem_ld32(t_row + hc * 64 + 32, r2);
                     tmem_ld_wait();
@@ -179,10 +209,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float inv = 1.0f;
                     const float* g = gamma_s;
                     if (section < 2) {
-                        float ss = 0.f;
+                        float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { float a = __uint_as_float(r[i]), b = __uint_as_float(r2[i]); ss += a * a + b * b; }
-                        inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
+                        for (int i = 0; i < 32; ++i) { float a = __uint_as_float(r[i]), b = __uint_as_float(r2[i]); ss[i & 3] += a * a + b * b; }
+                        inv = 8.0f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
                         g = gamma_s + (section * 8 + head) * 64;
                     }
                     if (row_ok) {
@@ -203,8 +233,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {  // EPI_GEGLU
                 uint32_t r2[32];
                 const int out_col0 = (n0 / BN) * (BN / 2);
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BN / 64; ++c) {
+                for (int c = half * (BN / 128); c < (half + 1) * (BN / 128); ++c) {
                     tmem_ld32(t_row + c * 32, r);              // h part
                     tmem_ld32(t_row + BN / 2 + c * 32, r2);    // g part
                     tmem_ld_wait();
