@@ -56,7 +56,7 @@ PROTOTYPES = {
     "rap_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _f32p, _f32p, _vp, _f32p, _vp]),
     "rap_test_ln_modulate": (C.c_int, [_f32p, _vp, C.c_int, _f32p, _f32p, C.c_int, _vp, C.c_float, _vp]),
     "rap_debug_read": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
-    "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, _vp]),
+    "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in PROTOTYPES.items():
     _fn = getattr(lib, _name)           # AttributeError here = header/library mismatch

@@ -352,7 +352,7 @@ __global__ void sampler_timesteps_kernel(float* t, int num_steps) {   // t_i = 1
 
 void build_tiles(const std::vector<int>& cu, std::vector<int4>& tiles) {
     for (size_t s = 0; s + 1 < cu.size(); ++s)
-        for (int q = cu[s]; q < cu[s + 1]; q += 128) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
+        for (int q = cu[s]; q < cu[s + 1]; q += 256) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
 }
 
 }  // namespace
@@ -583,7 +583,7 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, void* stream) {
+extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, void* dbg, void* stream) {
     RAP_REQUIRE(heads == HEADS, "rap_test_fmha: heads must be 8");
     std::vector<int> cu(cu_host, cu_host + n_segments + 1);
     std::vector<int4> tiles;
@@ -595,7 +595,7 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
     int rc = make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128);
     if (!rc) {
         FmhaArgs f{};
-        f.tiles = dt; f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f;
+        f.tiles = dt; f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
         rc = launch_fmha(tm, f, (int)tiles.size(), heads, static_cast<cudaStream_t>(stream));
     }
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));

@@ -3,30 +3,36 @@
 // reference at flow_model/layer.py:106-111 (part-wise: segments = views) and :123-128 (global:
 // segments = scenes).  The two calls differ only in the segment table, so this is one kernel.
 //
-// One CTA = one 128-row query tile of one head; two CTAs are resident per SM (112.1 KB smem,
-// 256 TMEM columns each) so one CTA's UMMAs run under the other's softmax.
-//   warp 0 : TMA producer  (Q once; K and V tiles through separate 2-deep rings)
-//   warp 1 : UMMA issuer   (S = Q K^T into TMEM cols [0,128); O += P V into cols [128,192))
-//   warps 2-5: softmax     (thread = query row: tcgen05.ld S, online max/sum, P -> smem as fp16 in
-//                           the K-major SWIZZLE_128B layout UMMA reads, lazy O rescale in TMEM)
+// One CTA = one 256-row query block (two 128-row tiles) of one head, one CTA per SM (193 KB smem, 512 TMEM columns).
+//   warp 0   : TMA producer  (Q tiles once; K and V blocks through separate 3-deep rings)
+//   warp 1   : UMMA issuer   (S_t = Q_t K^T into TMEM cols [128t,128t+128); O_t += P_t V into cols [256+64t, ...))
+//   warps 2-5: softmax of tile 0, warps 6-9: softmax of tile 1 (thread = query row: tcgen05.ld S, online max/sum in the
+//              log2 domain, P -> smem as fp16 in the K-major SWIZZLE_128B layout UMMA reads, lazy O rescale in TMEM)
 #include "fmha.cuh"
 #include "sm100.cuh"
 
 namespace rap {
 namespace {
 
+#define FMHA_TS(slot) do { if (dbg_on) p.dbg[(size_t)j * 16 + (slot)] = clock64(); } while (0)
+
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;         // 16 KB: 128 rows x 128 bytes
-constexpr int P_BYTES = BQ * BKV * 2;            // 32 KB: two 64-column K-major slabs
-constexpr int KV_STAGES = 2;
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KV_STAGES * TILE_BYTES, OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int kThreads = 192;
-constexpr uint32_t TMEM_COLS = 256, TM_S = 0, TM_O = 128;
-static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
+constexpr int KV_STAGES = 4;
+constexpr int OFF_Q = 0, OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
+constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int kThreads = 320;                    // TMA warp, UMMA warp, 2 x 4 softmax warps
+// TMEM columns of query tile t: S (fp32 scores) [256t, +128), P (fp16 pairs) [256t+128, +64), O (fp32) [256t+192, +64)
+constexpr uint32_t TMEM_COLS = 512, TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
+constexpr float kLazyMax = 8.0f;                 // rescale only if a row max grows by more than 2^8 (P stays <= 256 in fp16)
+static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
-__global__ void __launch_bounds__(kThreads, 2)
+// One CTA = one 256-row query block (two 128-row tiles t=0,1) of one head; one CTA per SM.
+// The UMMA warp ping-pongs between the two tiles -- QK0, PV0, QK1, PV1 per K/V block -- so while softmax warpgroup 0
+// exponentiates block j of tile 0, the tensor core produces tile 1's scores and vice versa: the exp (MUFU) pipe, which
+// bounds head_dim-64 attention, stays busy and each K/V block is fetched once for 256 query rows.
+__global__ void __launch_bounds__(kThreads, 1)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -35,178 +41,239 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const int4 w = p.tiles[blockIdx.x];            // {q_row0, seg_start, seg_end, -}
     const int q0 = w.x, kv_begin = w.y, kv_end = w.z;
     const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
+    const bool two = q0 + BQ < kv_end;             // second 128-row tile has rows inside the segment
 
     const uint32_t bar = sbase + OFF_BAR;
-    const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 24, v_full = bar + 40, v_empty = bar + 56;
-    const uint32_t s_full = bar + 72, p_full = bar + 80, pv_done = bar + 88, tmem_slot = bar + 96;
+    const uint32_t q_full = bar;
+    auto k_full = [&](int s) { return bar + 8 + 8 * s; };
+    auto k_empty = [&](int s) { return bar + 40 + 8 * s; };
+    auto v_full = [&](int s) { return bar + 72 + 8 * s; };
+    auto v_empty = [&](int s) { return bar + 104 + 8 * s; };
+    auto s_full = [&](int t) { return bar + 136 + 8 * t; };
+    auto p_full = [&](int t) { return bar + 152 + 8 * t; };
+    auto pv_done = [&](int t) { return bar + 168 + 8 * t; };
+    const uint32_t tmem_slot = bar + 200;
 
     if (threadIdx.x == 0) {
         if (sbase & 1023u) { atomicCAS(&g_dev_error, 0u, 0xA1u); __trap(); }
         tma_prefetch_desc(&tm_qkv);
         mbar_init(q_full, 1);
-        for (int s = 0; s < KV_STAGES; ++s) {
-            mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
-            mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
-        }
-        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 96);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 200);
 
     const int col_q = head * HD, col_k = p.d_model + head * HD, col_v = 2 * p.d_model + head * HD;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(q_full, TILE_BYTES);
+        const bool leader = elect_one();
+        if (leader) {
+            mbar_expect_tx(q_full, two ? 2 * TILE_BYTES : TILE_BYTES);
             tma_load_2d(sbase + OFF_Q, &tm_qkv, q_full, col_q, q0);
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j & 1; const uint32_t ph = (j >> 1) & 1;
-                const int row = kv_begin + j * BKV;
-                mbar_wait(k_empty + 8 * s, ph ^ 1, 0x41);
-                mbar_expect_tx(k_full + 8 * s, TILE_BYTES);
-                tma_load_2d(sbase + OFF_K + s * TILE_BYTES, &tm_qkv, k_full + 8 * s, col_k, row);
-                mbar_wait(v_empty + 8 * s, ph ^ 1, 0x42);
-                mbar_expect_tx(v_full + 8 * s, TILE_BYTES);
-                tma_load_2d(sbase + OFF_V + s * TILE_BYTES, &tm_qkv, v_full + 8 * s, col_v, row);
+            if (two) tma_load_2d(sbase + OFF_Q + TILE_BYTES, &tm_qkv, q_full, col_q, q0 + BQ);
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < n_kv; ++j) {
+            const int row = kv_begin + j * BKV;
+            mbar_wait(k_empty(s), ph ^ 1, 0x41);
+            if (leader) {
+                mbar_expect_tx(k_full(s), TILE_BYTES);
+                tma_load_2d(sbase + OFF_K + s * TILE_BYTES, &tm_qkv, k_full(s), col_k, row);
             }
+            mbar_wait(v_empty(s), ph ^ 1, 0x42);
+            if (leader) {
+                mbar_expect_tx(v_full(s), TILE_BYTES);
+                tma_load_2d(sbase + OFF_V + s * TILE_BYTES, &tm_qkv, v_full(s), col_v, row);
+            }
+            if (++s == KV_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV, false, false);   // A=Q K-major, B=K K-major, N=128
-            constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A=P K-major, B=V MN-major, N=64
-            const uint64_t dq = umma_desc_sw128(sbase + OFF_Q, 1024);
-            auto issue_qk = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(k_full + 8 * s, (j >> 1) & 1, 0x51);
-                tc_fence_after();
-                const uint64_t dk = umma_desc_sw128(sbase + OFF_K + s * TILE_BYTES, 1024);
+        // Whole warp converged; only the UMMA / commit instructions are predicated on the elected lane.
+        const bool leader = elect_one();
+        const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && leader;
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV, false, false);   // A=Q K-major, B=K K-major, N=128
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A=P K-major, B=V MN-major, N=64
+        const int nt = two ? 2 : 1;
+        auto issue_qk = [&](int t, int s) {
+            const uint64_t dq = umma_desc_sw128(sbase + OFF_Q + t * TILE_BYTES, 1024);
+            const uint64_t dk = umma_desc_sw128(sbase + OFF_K + s * TILE_BYTES, 1024);
+            if (leader) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem + TM_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-                umma_commit(s_full);
-                umma_commit(k_empty + 8 * s);
-            };
-            mbar_wait(q_full, 0, 0x50);
-            issue_qk(0);
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j & 1;
-                mbar_wait(p_full, j & 1, 0x52);          // P_j in smem, S_j consumed, O rescaled
-                tc_fence_after();
-                if (j + 1 < n_kv) issue_qk(j + 1);       // next scores first: softmax j+1 can start while PV_j runs
-                mbar_wait(v_full + 8 * s, (j >> 1) & 1, 0x53);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    const uint64_t dp = umma_desc_sw128(sbase + OFF_P + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 1024);
-                    const uint64_t dv = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES + k * 2048, 1024);
-                    umma_f16_ss(tmem + TM_O, dp, dv, idesc_pv, (j | k) != 0);
-                }
-                umma_commit(pv_done);
-                umma_commit(v_empty + 8 * s);
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem + t * TM_TILE + TM_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                umma_commit(s_full(t));
             }
+        };
+        mbar_wait(q_full, 0, 0x50);
+        mbar_wait(k_full(0), 0, 0x51);
+        tc_fence_after();
+        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
+        if (leader) umma_commit(k_empty(0));
+        int s = 0; uint32_t ph = 0;                      // stage / phase of K/V block j
+        for (int j = 0; j < n_kv; ++j) {
+            const int s1 = (s + 1 == KV_STAGES) ? 0 : s + 1;
+            const uint32_t ph1 = (s + 1 == KV_STAGES) ? ph ^ 1 : ph;
+            const bool more = j + 1 < n_kv;
+            const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES, 1024);
+            for (int t = 0; t < nt; ++t) {
+                mbar_wait(p_full(t), j & 1, 0x52);       // P_t(j) in TMEM, S_t(j) consumed, O_t rescaled if needed
+                tc_fence_after();
+                FMHA_TS(8 + 4 * t);
+                if (more) {                              // next scores of this tile first: its softmax can restart at once
+                    if (t == 0) { mbar_wait(k_full(s1), ph1, 0x53); tc_fence_after(); }
+                    issue_qk(t, s1);
+                    if (t == nt - 1 && leader) umma_commit(k_empty(s1));
+                }
+                FMHA_TS(9 + 4 * t);
+                if (t == 0) { mbar_wait(v_full(s), ph, 0x54); tc_fence_after(); }
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k)   // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 rows (encoded >> 4)
+                        umma_f16_ts(tmem + t * TM_TILE + TM_O, tmem + t * TM_TILE + TM_P + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+                    umma_commit(pv_done(t));
+                    if (t == nt - 1) umma_commit(v_empty(s));
+                }
+                FMHA_TS(10 + 4 * t);
+            }
+            s = s1; ph = ph1;
         }
     } else {
+        const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
         const int qd = warp & 3;                         // TMEM lane quarter of this warp
         const int r = qd * 32 + lane;                    // query row inside the tile
-        const uint32_t t_lane = tmem + (uint32_t(qd * 32) << 16);
-        const float sl2 = p.scale_log2;
-        float m_run = -INFINITY, l_run = 0.f;
-        uint32_t sreg[4][32];
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(s_full, j & 1, 0x61);
-            tc_fence_after();
+        if (t == 0 || two) {
+            const uint32_t t_lane = tmem + (uint32_t(qd * 32) << 16);
+            const uint32_t tm_s = t_lane + t * TM_TILE + TM_S, tm_p = t_lane + t * TM_TILE + TM_P, tm_o = t_lane + t * TM_TILE + TM_O;
+            const float sl2 = p.scale_log2;
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+            float m_run = -INFINITY, l_run = 0.f;      // m_run: reference exponent (log2 domain), only raised lazily
+            uint32_t sreg[4][32];
+            for (int j = 0; j < n_kv; ++j) {
+                FMHA_TS(0);
+                mbar_wait(s_full(t), j & 1, 0x61);
+                tc_fence_after();
+                FMHA_TS(1);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(t_lane + TM_S + c * 32, sreg[c]);
-            tmem_ld_wait();
-            const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
-            if (valid < BKV) {
+                for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + c * 32, sreg[c]);
+                tmem_ld_wait();
+                FMHA_TS(2);
+                const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
+                if (valid < BKV) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) sreg[c][i] = 0xff800000u;   // -inf
+                }
+                if (j == 0) {                                        // first block: exact row max as the reference exponent
+                    float mxa[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
+                    m_run = sl2 * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+                }
+                FMHA_TS(3);
+                // One pass: exponentials against the (possibly stale) reference exponent, block max tracked alongside.
+                float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                uint32_t preg[64];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) sreg[c][i] = 0xff800000u;   // -inf
-            }
-            // Row max / row sum with 8 independent accumulators: a single dependent FMNMX/FADD chain over 128 columns
-            // is latency-bound with only two softmax warps per scheduler.
-            float mxa[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
-            const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-            const float m_new = fmaxf(m_run, mx * sl2);
-            const float alpha = ex2f(m_run - m_new);
-            const bool grew = m_new > m_run;
-            m_run = m_new;
-            float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            uint32_t preg[64];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float a = ex2f(fmaf(__uint_as_float(sreg[c][i]), sl2, -m_new));
-                    const float b = ex2f(fmaf(__uint_as_float(sreg[c][i + 1]), sl2, -m_new));
-                    ls[(i >> 1) & 7] += a + b;
-                    preg[c * 16 + i / 2] = pack_half2(a, b);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float s0 = __uint_as_float(sreg[c][i]), s1 = __uint_as_float(sreg[c][i + 1]);
+                        bm[(i >> 1) & 3] = fmaxf(bm[(i >> 1) & 3], fmaxf(s0, s1));
+                        const float a = ex2f(fmaf(s0, sl2, -m_run));
+                        const float b = ex2f(fmaf(s1, sl2, -m_run));
+                        ls[(i >> 1) & 7] += a + b;
+                        preg[c * 16 + i / 2] = pack_half2(a, b);
+                    }
+                float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+                const float bmax = sl2 * fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
+                const bool grow = bmax > m_run + kLazyMax;
+                FMHA_TS(4);
+                if (j > 0) {
+                    mbar_wait(pv_done(t), (j - 1) & 1, 0x62);        // PV_t(j-1) retired: P columns free, O stable
+                    tc_fence_after();
                 }
-            const float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
-            l_run = l_run * alpha + lsum;
-
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1, 0x62);           // PV_{j-1} retired: P buffer free, O readable
-                tc_fence_after();
-                if (__any_sync(0xffffffffu, grew)) {
-                    uint32_t o[32];
+                if (__any_sync(0xffffffffu, grow)) {
+                    // Rare slow path (a row max jumped by > 2^8): raise that row's exponent, redo this block from the scores
+                    // still in TMEM, and rescale its O / l.  (Rows whose exponent did not move recompute identical values.)
+                    const float m_new = grow ? bmax : m_run;
+                    const float alpha = ex2f(m_run - m_new);
+                    m_run = m_new;
+                    l_run *= alpha;
+                    lsum = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        tmem_ld32(t_lane + TM_O + c * 32, o);
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(t_lane + TM_O + c * 32, o);
+                        for (int i = 0; i < 32; i += 2) {
+                            const bool v0 = c * 32 + i < valid, v1 = c * 32 + i + 1 < valid;
+                            const float a = v0 ? ex2f(fmaf(__uint_as_float(sreg[0][i]), sl2, -m_run)) : 0.f;
+                            const float b = v1 ? ex2f(fmaf(__uint_as_float(sreg[0][i + 1]), sl2, -m_run)) : 0.f;
+                            lsum += a + b;
+                            preg[c * 16 + i / 2] = pack_half2(a, b);
+                        }
                     }
+                    if (j > 0) {
+                        uint32_t o[8];
+#pragma unroll 1
+                        for (int c = 0; c < HD / 8; ++c) {
+                            tmem_ld8(tm_o + c * 8, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st8(tm_o + c * 8, o);
+                        }
+                    }
+                }
+                l_run += lsum;
+                FMHA_TS(5);
+                // P row -> TMEM (fp16 pairs, 64 columns): the A operand of the P.V UMMA
+                {
+                    uint32_t (&plo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&preg[0]);
+                    uint32_t (&phi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&preg[32]);
+                    tmem_st32(tm_p, plo);
+                    tmem_st32(tm_p + 32, phi);
                     tmem_st_wait();
                 }
+                FMHA_TS(6);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(t));
+                FMHA_TS(7);
             }
-            // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7), two 64-column slabs.
-            const uint32_t prow = sbase + OFF_P + r * 128;
+            // epilogue: O / l -> fp16
+            mbar_wait(pv_done(t), (n_kv - 1) & 1, 0x63);
+            tc_fence_after();
+            const float inv_l = 1.0f / l_run;
+            const int row = q0 + t * BQ + r;
+            uint32_t o[32], o2[32];
+            tmem_ld32(tm_o, o);
+            tmem_ld32(tm_o + 32, o2);
+            tmem_ld_wait();
+            if (row < kv_end) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
 #pragma unroll
-            for (int ch = 0; ch < 16; ++ch) {
-                const uint32_t addr = prow + (ch >> 3) * (P_BYTES / 2) + (((ch & 7) ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(preg[4 * ch]), "r"(preg[4 * ch + 1]),
-                             "r"(preg[4 * ch + 2]), "r"(preg[4 * ch + 3]) : "memory");
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // epilogue: O / l -> fp16
-        mbar_wait(pv_done, (n_kv - 1) & 1, 0x63);
-        tc_fence_after();
-        const float inv_l = 1.0f / l_run;
-        const int row = q0 + r;
-        uint32_t o[32], o2[32];
-        tmem_ld32(t_lane + TM_O, o);
-        tmem_ld32(t_lane + TM_O + 32, o2);
-        tmem_ld_wait();
-        if (row < kv_end) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                dst[i / 8] = make_uint4(pack_half2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l),
-                                        pack_half2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l),
-                                        pack_half2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l),
-                                        pack_half2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l));
-                dst[4 + i / 8] = make_uint4(pack_half2(__uint_as_float(o2[i]) * inv_l, __uint_as_float(o2[i + 1]) * inv_l),
-                                            pack_half2(__uint_as_float(o2[i + 2]) * inv_l, __uint_as_float(o2[i + 3]) * inv_l),
-                                            pack_half2(__uint_as_float(o2[i + 4]) * inv_l, __uint_as_float(o2[i + 5]) * inv_l),
-                                            pack_half2(__uint_as_float(o2[i + 6]) * inv_l, __uint_as_float(o2[i + 7]) * inv_l));
+                for (int i = 0; i < 32; i += 8) {
+                    dst[i / 8] = make_uint4(pack_half2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l));
+                    dst[4 + i / 8] = make_uint4(pack_half2(__uint_as_float(o2[i]) * inv_l, __uint_as_float(o2[i + 1]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 2]) * inv_l, __uint_as_float(o2[i + 3]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 4]) * inv_l, __uint_as_float(o2[i + 5]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 6]) * inv_l, __uint_as_float(o2[i + 7]) * inv_l));
+                }
             }
         }
     }

@@ -5,10 +5,11 @@
 namespace rap {
 
 struct FmhaArgs {
-    const int4* tiles;   // device: {q_row0, seg_start, seg_end, 0} per 128-row query tile
+    const int4* tiles;   // device: {q_row0, seg_start, seg_end, 0} per 256-row query block (two 128-row tiles)
     __half* out;         // [T, d_model] fp16, head h at columns [64h, 64h+64)
     int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
     float scale_log2;    // log2(e) / sqrt(head_dim)
+    long long* dbg;      // optional clock64() timeline of CTA (0,0): [iter][16] slots (tools/fmha_timeline.py), else null
 };
 
 // tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.

@@ -78,44 +78,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
+        // ------------------------------------------------------------ TMA producer (warp converged, one elected lane issues)
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
+                if (leader) {
                     mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
                     tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ UMMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1, 0x21);
+        // ------------------------------------------------------------ UMMA issuer (warp converged: descriptors stay warp-uniform)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1, 0x21);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase, 0x22);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase, 0x22);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-                    const uint64_t da = umma_desc_sw128(sa, 1024), db = umma_desc_sw128(sa + A_STAGE_BYTES, 1024);
+                const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                const uint64_t da = umma_desc_sw128(sa, 1024), db = umma_desc_sw128(sa + A_STAGE_BYTES, 1024);
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)   // +32 bytes (encoded +2) per K=16 step inside the swizzle row
                         umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(empty_bar(stage));       // frees the smem stage when these MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));             // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) umma_commit(tfull_bar(acc));     // accumulator ready for the epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ------------------------------------------------------------ epilogue: 8 warps.  TMEM lane quarter = warp % 4

@@ -95,7 +95,7 @@ def test_fmha_varlen(rap, lens):
     qkv = qkv.half().contiguous()
     out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array(cu), len(lens), out.data_ptr(), rap.stream_ptr()), "rap_test_fmha")
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array(cu), len(lens), out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
     _sync_check(rap)
     ref = torch.empty(T, 8, 64, device="cuda")
     for s, e in zip(cu[:-1], cu[1:]):
