@@ -93,7 +93,7 @@ const char* rap_profile_class_name(int kernel_class);
 
 /* Micro entry points used by tests/ and profiling to exercise one kernel at a time. */
 int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
-                  const float* addend, float* out32, void* out16, const float* gamma, void* stream);
+                  const float* addend, float* out32, void* out16, const float* gamma, void* dbg, void* stream);
 /* dbg: optional device buffer of n_kv_blocks*16 int64 receiving a clock64() timeline of CTA (0,0), or NULL. */
 int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out_f16,
                   void* dbg, void* stream);

@@ -573,13 +573,13 @@ extern "C" int rap_plan_rigidify(rap_plan_t* pl, const float* prediction, const 
 
 // ======================================================================================= micro entry points
 extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A, const void* W, const float* bias, const float* addend,
-                             float* out32, void* out16, const float* gamma, void* stream) {
+                             float* out32, void* out16, const float* gamma, void* dbg, void* stream) {
     CUtensorMap ta, tb;
     RAP_TRY(make_tmap_f16_sw128(&ta, A, M, K, K, 128));
     RAP_TRY(make_tmap_f16_sw128(&tb, W, N, K, K, bn));
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
-    g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N;
+    g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
 }
 

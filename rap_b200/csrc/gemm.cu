@@ -17,21 +17,28 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 fp16 = one 128-byte swizzle row
 constexpr int kThreads = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+// Epilogue staging: each epilogue warp owns 32 rows x 128 B (+16 B pad: conflict-free 16-byte accesses in both directions).
+// Accumulator rows leave TMEM one row per thread; going through this buffer turns every global access into 4 rows x 128
+// contiguous bytes per warp instruction instead of 32 rows x 16 B (which costs 32 LSU cycles per instruction).
+constexpr int STG_ROW_BYTES = 144;
+constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;
 
 template <int BN> struct Cfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 3 : 5;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/ + 4096 /*gamma*/;
+    static constexpr int GAMMA_BYTES = 4096;
+    static constexpr int STG_OFF = STAGES * STAGE_BYTES + BAR_BYTES + GAMMA_BYTES;
+    static constexpr int SMEM_BYTES = STG_OFF + 8 * STG_WARP_BYTES + 1024 /*align slack*/;
 };
 
 // Exact (erf) GELU.  1+erf(z) through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 output grid):
 //   z>=0: 2 - poly(t) e^{-z^2},  z<0: poly(t) e^{-z^2},  t = 1/(1 + 0.3275911 |z|)   -- one rcp, one ex2, 7 FMAs.
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = x * 0.70710678118654752f, az = fabsf(z);
-    const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));   // MUFU.RCP, not the IEEE software path
     float pl = fmaf(1.061405429f, t, -1.453152027f);
     pl = fmaf(pl, t, 1.421413741f);
     pl = fmaf(pl, t, -0.284496736f);
@@ -39,7 +46,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float e = pl * t * ex2f(-az * az * 1.4426950408889634f);
     return 0.5f * x * (z >= 0.f ? 2.0f - e : e);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -77,12 +84,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
+    const bool dbg_cta = p.dbg && blockIdx.x == 0;
+    int dbg_tile = 0;
+#define GEMM_TS(slot) do { if (dbg_cta && lane == 0) p.dbg[(size_t)dbg_tile * 8 + (slot)] = clock64(); } while (0)
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (warp converged, one elected lane issues)
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            GEMM_TS(0);
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
                 if (leader) {
@@ -93,15 +104,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            GEMM_TS(1);
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ UMMA issuer (warp converged: descriptors stay warp-uniform)
         const bool leader = elect_one();
         constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
+            GEMM_TS(2);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1, 0x21);
             tc_fence_after();
+            GEMM_TS(3);
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < k_blocks; ++kb) {
                 mbar_wait(full_bar(stage), phase, 0x22);
@@ -117,6 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             if (leader) umma_commit(tfull_bar(acc));     // accumulator ready for the epilogue
+            GEMM_TS(4);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
@@ -124,139 +139,160 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // (hardware rule), column half = (warp - 2) / 4, so two warps share a quarter and split the tile's columns.
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        constexpr int HC = BN / 2;                       // columns per warp
+        constexpr int HC = BN / 2;                       // accumulator columns per warp
+        const uint32_t stg = smem_base + C::STG_OFF + (warp - 2) * STG_WARP_BYTES;
+        const uint32_t stg_w = stg + lane * STG_ROW_BYTES;                          // write side: thread = row
+        const int rr0 = lane >> 3, cc = lane & 7;                                   // read side: 4 rows x 8 x 16 B per instruction
+        const uint32_t stg_r = stg + rr0 * STG_ROW_BYTES + cc * 16;
+        auto sts4 = [](uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+        };
+        auto lds4 = [](uint32_t addr) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+            return v;
+        };
+        const bool dbg_w = warp == 2;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            if (dbg_w) GEMM_TS(5);
+            const int row_base = m0 + q * 32;            // first of this warp's 32 rows
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
             uint32_t r[32];
 
             if constexpr (EPI == EPI_F32) {
-                // Prefetch the addend (residual / static embedding) row segment into registers BEFORE waiting for the
-                // accumulator: the loads fly under this tile's MMAs instead of serialising with the TMEM reads.
+                // Residual / static-embedding rows prefetched (coalesced) BEFORE waiting for the accumulator: the loads fly
+                // under this tile's MMAs.  Layout of ad[c][it]: chunk c (32 columns), rows rr0 + 4*it, 4 columns at cc*4.
                 const int col0 = n0 + half * HC;
-                float4 ad[HC / 4];
-                if (p.addend && row_ok) {
-                    const float4* a4 = reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld32 + col0);
+                float4 ad[HC / 32][8];
 #pragma unroll
-                    for (int i = 0; i < HC / 4; ++i) ad[i] = a4[i];
-                } else {
+                for (int c = 0; c < HC / 32; ++c)
 #pragma unroll
-                    for (int i = 0; i < HC / 4; ++i) ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const float* tab = (p.table && row_ok) ? p.table + (size_t)(p.sel[row] ? 1 : 0) * p.N : nullptr;
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + rr0;
+                        ad[c][it] = (p.addend && row < p.M) ? *reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld32 + col0 + c * 32 + cc * 4)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 mbar_wait(tfull_bar(acc), acc_phase, 0x31);
                 tc_fence_after();
+                if (dbg_w) GEMM_TS(6);
 #pragma unroll
                 for (int c = 0; c < HC / 32; ++c) {
                     tmem_ld32(t_row + half * HC + c * 32, r);
                     tmem_ld_wait();
-                    if (row_ok) {
-                        const int col = col0 + c * 32;
-                        float* o = p.out32 + (size_t)row * p.ld32 + col;
-                        uint32_t h16[16];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) sts4(stg_w + k * 16, r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+                    __syncwarp();
+                    const int col = col0 + c * 32 + cc * 4;
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) b = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + rr0;
+                        const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
+                        const float4 a = ad[c][it];
+                        float4 v = make_float4(__uint_as_float(u.x) + a.x + b.x, __uint_as_float(u.y) + a.y + b.y, __uint_as_float(u.z) + a.z + b.z,
+                                               __uint_as_float(u.w) + a.w + b.w);
+                        if (row < p.M) {
+                            if (p.table) {
+                                const float4 t = *reinterpret_cast<const float4*>(p.table + (size_t)(p.sel[row] ? 1 : 0) * p.N + col);
+                                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                            }
+                            *reinterpret_cast<float4*>(p.out32 + (size_t)row * p.ld32 + col) = v;
+                            if (p.out16) *reinterpret_cast<uint2*>(p.out16 + (size_t)row * p.ld16 + col) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // fp16 outputs: each staging round holds 64 output columns (128 B per row).
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
+                if (dbg_w) GEMM_TS(6);
+                constexpr int ROUNDS = (EPI == EPI_GEGLU) ? 1 : HC / 64;    // GEGLU: 2 x (32 h + 32 g) -> 64 outputs per warp
+#pragma unroll 1
+                for (int rd = 0; rd < ROUNDS; ++rd) {
+                    uint32_t r2[32];
+                    uint32_t pk[32];                       // 64 fp16 outputs of this thread's row
+                    int out_col;                           // first output column of this round
+                    if constexpr (EPI == EPI_F16_SILU) {
+                        const int col = n0 + half * HC + rd * 64;
+                        out_col = col;
+                        tmem_ld32(t_row + half * HC + rd * 64, r);
+                        tmem_ld32(t_row + half * HC + rd * 64 + 32, r2);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 a = ad[c * 8 + i / 4];
-                            float4 v = make_float4(__uint_as_float(r[i]) + a.x, __uint_as_float(r[i + 1]) + a.y, __uint_as_float(r[i + 2]) + a.z,
-                                                   __uint_as_float(r[i + 3]) + a.w);
-                            if (p.bias) { float4 b = *reinterpret_cast<const float4*>(p.bias + col + i); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-                            if (tab) { float4 t = *reinterpret_cast<const float4*>(tab + col + i); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-                            *reinterpret_cast<float4*>(o + i) = v;
-                            h16[i / 2] = pack_half2(v.x, v.y);
-                            h16[i / 2 + 1] = pack_half2(v.z, v.w);
+                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col + i), b1 = *reinterpret_cast<const float4*>(p.bias + col + 32 + i);
+                            pk[i / 2] = pack_half2(silu(__uint_as_float(r[i]) + b0.x), silu(__uint_as_float(r[i + 1]) + b0.y));
+                            pk[i / 2 + 1] = pack_half2(silu(__uint_as_float(r[i + 2]) + b0.z), silu(__uint_as_float(r[i + 3]) + b0.w));
+                            pk[16 + i / 2] = pack_half2(silu(__uint_as_float(r2[i]) + b1.x), silu(__uint_as_float(r2[i + 1]) + b1.y));
+                            pk[16 + i / 2 + 1] = pack_half2(silu(__uint_as_float(r2[i + 2]) + b1.z), silu(__uint_as_float(r2[i + 3]) + b1.w));
                         }
-                        if (p.out16) {
-                            uint4* o16 = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
+                    } else if constexpr (EPI == EPI_QKV) {
+                        // One 64-column head per round.  section 0/1 = q/k (RMS-normalised), 2 = v.
+                        const int hc = half * (HC / 64) + rd;
+                        const int col = n0 + hc * 64;
+                        out_col = col;
+                        const int dmodel = p.N / 3, section = col / dmodel, head = (col % dmodel) / 64;
+                        tmem_ld32(t_row + hc * 64, r);
+                        tmem_ld32(t_row + hc * 64 + 32, r2);
+                        tmem_ld_wait();
+                        if (section < 2) {
+                            float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) o16[i] = make_uint4(h16[4 * i], h16[4 * i + 1], h16[4 * i + 2], h16[4 * i + 3]);
-                        }
-                    }
-                }
-            } else if constexpr (EPI == EPI_F16_SILU) {
-                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < HC / 32; ++c) {
-                    tmem_ld32(t_row + half * HC + c * 32, r);
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        const int col = n0 + half * HC + c * 32;
-                        uint4* o16 = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
+                            for (int i = 0; i < 32; ++i) { const float a = __uint_as_float(r[i]), b = __uint_as_float(r2[i]); ss[i & 3] += a * a + b * b; }
+                            const float inv = 8.0f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
+                            const float4* g4 = reinterpret_cast<const float4*>(gamma_s + (section * 8 + head) * 64);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = silu(__uint_as_float(r[i + j]) + p.bias[col + i + j]);
-                            o16[i / 8] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-                        }
-                    }
-                }
-            } else if constexpr (EPI == EPI_QKV) {
-                // One 64-column head per iteration.  section 0/1 = q/k (RMS-normalised), 2 = v.
-                const int dmodel = p.N / 3;
-                uint32_t r2[32];
-                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
-                tc_fence_after();
-#pragma unroll 1
-                for (int hc = half * (HC / 64); hc < (half + 1) * (HC / 64); ++hc) {
-                    tmem_ld32(t_row + hc * 64, r);
-                    tmem_ld32(t_row + hc * 64 + 32, r2);
-                    tmem_ld_wait();
-                    const int col = n0 + hc * 64;
-                    const int section = col / dmodel;
-                    const int head = (col % dmodel) / 64;
-                    float inv = 1.0f;
-                    const float* g = gamma_s;
-                    if (section < 2) {
-                        float ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) { float a = __uint_as_float(r[i]), b = __uint_as_float(r2[i]); ss[i & 3] += a * a + b * b; }
-                        inv = 8.0f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
-                        g = gamma_s + (section * 8 + head) * 64;
-                    }
-                    if (row_ok) {
-                        uint4* o16 = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + col);
-#pragma unroll
-                        for (int i = 0; i < 64; i += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int e = i + j;
-                                const float x = __uint_as_float(e < 32 ? r[e] : r2[e - 32]);
-                                v[j] = (section < 2) ? x * inv * g[e] : x;
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 g0 = g4[i / 4], g1 = g4[8 + i / 4];
+                                pk[i / 2] = pack_half2(__uint_as_float(r[i]) * inv * g0.x, __uint_as_float(r[i + 1]) * inv * g0.y);
+                                pk[i / 2 + 1] = pack_half2(__uint_as_float(r[i + 2]) * inv * g0.z, __uint_as_float(r[i + 3]) * inv * g0.w);
+                                pk[16 + i / 2] = pack_half2(__uint_as_float(r2[i]) * inv * g1.x, __uint_as_float(r2[i + 1]) * inv * g1.y);
+                                pk[16 + i / 2 + 1] = pack_half2(__uint_as_float(r2[i + 2]) * inv * g1.z, __uint_as_float(r2[i + 3]) * inv * g1.w);
                             }
-                            o16[i / 8] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                pk[i / 2] = pack_half2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                                pk[16 + i / 2] = pack_half2(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
+                            }
+                        }
+                    } else {  // EPI_GEGLU: this warp's two (h,g) chunk pairs -> 64 consecutive output columns
+                        out_col = (n0 / BN) * (BN / 2) + half * 64;
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+                            const int c = half * 2 + cp;
+                            tmem_ld32(t_row + c * 32, r);              // h part
+                            tmem_ld32(t_row + BN / 2 + c * 32, r2);    // g part
+                            tmem_ld_wait();
+                            const float* bh = p.bias + n0 + c * 32;
+                            const float* bg = p.bias + n0 + BN / 2 + c * 32;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 h4 = *reinterpret_cast<const float4*>(bh + i), g4 = *reinterpret_cast<const float4*>(bg + i);
+                                pk[cp * 16 + i / 2] = pack_half2((__uint_as_float(r[i]) + h4.x) * gelu_erf(__uint_as_float(r2[i]) + g4.x),
+                                                                 (__uint_as_float(r[i + 1]) + h4.y) * gelu_erf(__uint_as_float(r2[i + 1]) + g4.y));
+                                pk[cp * 16 + i / 2 + 1] = pack_half2((__uint_as_float(r[i + 2]) + h4.z) * gelu_erf(__uint_as_float(r2[i + 2]) + g4.z),
+                                                                     (__uint_as_float(r[i + 3]) + h4.w) * gelu_erf(__uint_as_float(r2[i + 3]) + g4.w));
+                            }
                         }
                     }
-                }
-            } else {  // EPI_GEGLU
-                uint32_t r2[32];
-                const int out_col0 = (n0 / BN) * (BN / 2);
-                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = half * (BN / 128); c < (half + 1) * (BN / 128); ++c) {
-                    tmem_ld32(t_row + c * 32, r);              // h part
-                    tmem_ld32(t_row + BN / 2 + c * 32, r2);    // g part
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        const float* bh = p.bias + n0 + c * 32;
-                        const float* bg = p.bias + n0 + BN / 2 + c * 32;
-                        uint4* o16 = reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + out_col0 + c * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            float v[8];
+                    for (int k = 0; k < 8; ++k) sts4(stg_w + k * 16, pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                    __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                v[j] = (__uint_as_float(r[i + j]) + bh[i + j]) * gelu_erf(__uint_as_float(r2[i + j]) + bg[i + j]);
-                            o16[i / 8] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-                        }
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + rr0;
+                        const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
+                        if (row < p.M) *reinterpret_cast<uint4*>(p.out16 + (size_t)row * p.ld16 + out_col + cc * 8) = u;
                     }
+                    __syncwarp();
                 }
             }
+            if (dbg_w) GEMM_TS(7);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));

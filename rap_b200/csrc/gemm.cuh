@@ -25,6 +25,7 @@ struct GemmArgs {
     const float* table;       // [2, N] row-select table (anchor embedding) or null
     const unsigned char* sel; // [M] row selector for `table`
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
+    long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
 };
 
 int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t st);

@@ -29,7 +29,7 @@ def _gemm(rap, epi, bn, A, W, bias=None, addend=None, gamma=None, out16_cols=Non
     out32 = torch.zeros(M, N, device="cuda") if epi == 0 else None
     out16 = torch.zeros(M, out16_cols or N, device="cuda", dtype=torch.float16) if (epi != 0 or out16_cols) else None
     rap.check(rap.lib.rap_test_gemm(epi, bn, M, N, K, A.data_ptr(), W.data_ptr(), rap.ptr(bias), rap.ptr(addend), rap.ptr(out32),
-                                    rap.ptr(out16), rap.ptr(gamma), rap.stream_ptr()), "rap_test_gemm")
+                                    rap.ptr(out16), rap.ptr(gamma), None, rap.stream_ptr()), "rap_test_gemm")
     _sync_check(rap)
     return out32, out16
 
