@@ -25,7 +25,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int kThreads = 320;                    // TMA warp, UMMA warp, 2 x 4 softmax warps
 // TMEM columns of query tile t: S (fp32 scores) [256t, +128), P (fp16 pairs) [256t+128, +64), O (fp32) [256t+192, +64)
 constexpr uint32_t TMEM_COLS = 512, TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
-constexpr float kLazyMax = 8.0f;                 // rescale only if a row max grows by more than 2^8 (P stays <= 256 in fp16)
+constexpr float kRowSumLimit = 32768.0f;         // a block row sum >= 2^15 means some P may leave the fp16 range: re-reference that row
 static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
 // One CTA = one 256-row query block (two 128-row tiles t=0,1) of one head; one CTA per SM.
@@ -52,6 +52,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     auto s_full = [&](int t) { return bar + 136 + 8 * t; };
     auto p_full = [&](int t) { return bar + 152 + 8 * t; };
     auto pv_done = [&](int t) { return bar + 168 + 8 * t; };
+    auto s_free = [&](int t) { return bar + 184 + 8 * t; };
     const uint32_t tmem_slot = bar + 200;
 
     if (threadIdx.x == 0) {
@@ -59,7 +60,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
         tma_prefetch_desc(&tm_qkv);
         mbar_init(q_full, 1);
         for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -120,16 +121,18 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             const bool more = j + 1 < n_kv;
             const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES, 1024);
             for (int t = 0; t < nt; ++t) {
-                mbar_wait(p_full(t), j & 1, 0x52);       // P_t(j) in TMEM, S_t(j) consumed, O_t rescaled if needed
-                tc_fence_after();
-                FMHA_TS(8 + 4 * t);
-                if (more) {                              // next scores of this tile first: its softmax can restart at once
-                    if (t == 0) { mbar_wait(k_full(s1), ph1, 0x53); tc_fence_after(); }
+                if (more) {                              // next scores of this tile as soon as its softmax is done with S_t(j)
+                    if (t == 0) mbar_wait(k_full(s1), ph1, 0x53);
+                    mbar_wait(s_free(t), j & 1, 0x55);
+                    tc_fence_after();
+                    FMHA_TS(8 + 4 * t);
                     issue_qk(t, s1);
                     if (t == nt - 1 && leader) umma_commit(k_empty(s1));
                 }
                 FMHA_TS(9 + 4 * t);
-                if (t == 0) { mbar_wait(v_full(s), ph, 0x54); tc_fence_after(); }
+                if (t == 0) mbar_wait(v_full(s), ph, 0x54);
+                mbar_wait(p_full(t), j & 1, 0x52);       // P_t(j) in TMEM, O_t rescaled if needed
+                tc_fence_after();
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; ++k)   // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 rows (encoded >> 4)
@@ -180,33 +183,44 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                     m_run = sl2 * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
                 }
                 FMHA_TS(3);
-                // One pass: exponentials against the (possibly stale) reference exponent, block max tracked alongside.
+                // One pass: exponentials against the (possibly stale) reference exponent.  No per-element max tracking: the only thing
+                // a stale reference can break is fp16 overflow of P, and any element >= 2^15 shows up in the block's row sum.
                 float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 uint32_t preg[64];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float s0 = __uint_as_float(sreg[c][i]), s1 = __uint_as_float(sreg[c][i + 1]);
-                        bm[(i >> 1) & 3] = fmaxf(bm[(i >> 1) & 3], fmaxf(s0, s1));
-                        const float a = ex2f(fmaf(s0, sl2, -m_run));
-                        const float b = ex2f(fmaf(s1, sl2, -m_run));
+                        const float a = ex2f(fmaf(__uint_as_float(sreg[c][i]), sl2, -m_run));
+                        const float b = ex2f(fmaf(__uint_as_float(sreg[c][i + 1]), sl2, -m_run));
                         ls[(i >> 1) & 7] += a + b;
                         preg[c * 16 + i / 2] = pack_half2(a, b);
                     }
                 float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
-                const float bmax = sl2 * fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
-                const bool grow = bmax > m_run + kLazyMax;
+                const bool grow = !(lsum < kRowSumLimit);            // also catches inf / NaN
+                const bool slow = __any_sync(0xffffffffu, grow);
+                if (!slow) {                                         // common case: the scores are consumed, let the tensor core
+                    tc_fence_before();                               // overwrite S_t with block j+1 while P_t(j) is being stored
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
                 FMHA_TS(4);
                 if (j > 0) {
                     mbar_wait(pv_done(t), (j - 1) & 1, 0x62);        // PV_t(j-1) retired: P columns free, O stable
                     tc_fence_after();
                 }
-                if (__any_sync(0xffffffffu, grow)) {
-                    // Rare slow path (a row max jumped by > 2^8): raise that row's exponent, redo this block from the scores
-                    // still in TMEM, and rescale its O / l.  (Rows whose exponent did not move recompute identical values.)
-                    const float m_new = grow ? bmax : m_run;
+                if (slow) {
+                    // Rare slow path (some score exceeded the reference by ~2^15): take this block's exact row max as the new
+                    // reference, redo the block from the scores still in TMEM, and rescale O / l.  (Rows that did not overflow
+                    // keep their reference and recompute identical values.)
+                    float bmax = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, (c * 32 + i < valid) ? __uint_as_float(sreg[0][i]) : -INFINITY);
+                    }
+                    const float m_new = grow ? bmax * sl2 : m_run;
                     const float alpha = ex2f(m_run - m_new);
                     m_run = m_new;
                     l_run *= alpha;
@@ -235,6 +249,9 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                             tmem_st8(tm_o + c * 8, o);
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free(t));
                 }
                 l_run += lsum;
                 FMHA_TS(5);

@@ -105,6 +105,25 @@ def test_fmha_varlen(rap, lens):
     assert err < 1e-2, f"max err {err}"
 
 
+def test_fmha_lazy_reference_overflow_path(rap):
+    """Adversarial scores for the lazy reference exponent: the first K/V block scores ~0, later blocks reach 2^40 times more, so
+    the stale-reference pass must detect fp16 overflow of P and take the re-reference + O/l rescale path (several times)."""
+    g = torch.Generator("cuda").manual_seed(11)
+    T = 1024
+    qkv = torch.randn(T, 3, 8, 64, device="cuda", generator=g)
+    qkv[:, :2] = F.normalize(qkv[:, :2], dim=-1) * 16            # |q| = |k| = 16: scaled scores up to 46 in log2 units
+    qkv[:128, 1] *= 1e-3                                         # block 0 keys ~ 0 -> reference exponent 0
+    qkv[128:384, 1] *= 0.3                                       # intermediate growth
+    qkv = qkv.half().contiguous()
+    out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array([0, T]), 1, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
+    _sync_check(rap)
+    q, k, v = (qkv[:, i].float().transpose(0, 1) for i in range(3))
+    ref = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float().view(T, 8, 64) - ref).abs().max().item() < 2e-2
+
+
 def test_procrustes_kat(rap, golden_dir):
     from rap_b200.rectified_point_flow import procrustes
     g = np.load(os.path.join(golden_dir, "procrustes_kat.npz"))
