@@ -102,6 +102,15 @@ namespace {
 
 constexpr int D = 512, HEADS = 8, HD = 64, FF_INNER = 2048, ADA_CH = 256;
 
+// |q| <= 8 max|gamma_q|, |k| <= 8 max|gamma_k| after the RMS norm (norm.py:33)  =>  |q.k| log2(e)/8 <= 64 gq gk log2(e)/8.
+__global__ void score_bound_kernel(const float* gamma /* [2][8][64] */, float* bound /* [8] */) {
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gq = 0.f, gk = 0.f;
+    for (int c = lane; c < 64; c += 32) { gq = fmaxf(gq, fabsf(gamma[h * 64 + c])); gk = fmaxf(gk, fabsf(gamma[512 + h * 64 + c])); }
+    for (int o = 16; o; o >>= 1) { gq = fmaxf(gq, __shfl_xor_sync(0xffffffffu, gq, o)); gk = fmaxf(gk, __shfl_xor_sync(0xffffffffu, gk, o)); }
+    if (lane == 0) bound[h] = 64.0f * gq * gk * (1.4426950408889634f / 8.0f) * 1.001f;
+}
+
 struct WeightEntry {
     void* dst = nullptr;
     bool half = false;
@@ -133,6 +142,7 @@ struct rap_dit {
     // per layer
     std::vector<__half*> wqkv[2], wout[2], w1, w2;
     std::vector<float*> bout[2], gamma[2] /* [2(q,k),8,64] */, b1, b2, ffn_w, ffn_b;
+    float* score_bound = nullptr;   // [2L][8]: per (layer, block, head) bound of |q.k| * log2(e)/8 implied by the qk-norm gammas
     // AdaLN MLPs, module m = 2*layer + blk
     __half *ada_w1 = nullptr, *ada_w2 = nullptr, *ada_w3 = nullptr;
     float *ada_b1 = nullptr, *ada_b2 = nullptr, *ada_b3 = nullptr;
@@ -248,6 +258,7 @@ extern "C" int rap_dit_create(rap_dit_t** out, int embed_dim, int num_layers, in
         add_entry(d, p + "ff.net.2.weight", d->w2[l], true, plain(D, FF_INNER), (int64_t)D * FF_INNER);
         add_entry(d, p + "ff.net.2.bias", d->b2[l], false, plain(1, D), D);
     }
+    d->score_bound = s.take<float>((size_t)M * HEADS);
     d->wh0 = s.take<__half>((size_t)D * D); d->bh0 = s.take<float>(D);
     d->wh2 = s.take<__half>((size_t)(D / 2) * D); d->bh2 = s.take<float>(D / 2);
     d->wh4 = s.take<float>(3 * (D / 2));
@@ -314,6 +325,7 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
     d->tm_w1.resize(L); d->tm_w2.resize(L);
     for (int l = 0; l < L; ++l) {
         for (int b = 0; b < 2; ++b) {
+            score_bound_kernel<<<1, 256>>>(d->gamma[b][l], d->score_bound + (size_t)(2 * l + b) * HEADS);
             RAP_TRY(make_tmap_f16_sw128(&d->tm_qkv[b][l], d->wqkv[b][l], 3 * D, D, D, 256));
             RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, 128));
         }
@@ -482,6 +494,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
             FmhaArgs f{};
             f.tiles = b == 0 ? pl->tiles_part : pl->tiles_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
+            f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_tiles_part : pl->n_tiles_batch, HEADS, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;

@@ -25,6 +25,9 @@ constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int kThreads = 320;                    // TMA warp, UMMA warp, 2 x 4 softmax warps
 // TMEM columns of query tile t: S (fp32 scores) [256t, +128), P (fp16 pairs) [256t+128, +64), O (fp32) [256t+192, +64)
 constexpr uint32_t TMEM_COLS = 512, TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
+// Handing S back before the exponentials (possible whenever the gamma bound excludes overflow) was MEASURED slower: both query
+// tiles then run in lockstep and fight for the MUFU pipe, while the release-after-exp order staggers them naturally.
+constexpr bool kEarlyRelease = false;
 constexpr float kRowSumLimit = 32768.0f;         // a block row sum >= 2^15 means some P may leave the fp16 range: re-reference that row
 static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
@@ -153,6 +156,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             const uint32_t tm_s = t_lane + t * TM_TILE + TM_S, tm_p = t_lane + t * TM_TILE + TM_P, tm_o = t_lane + t * TM_TILE + TM_O;
             const float sl2 = p.scale_log2;
             const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+            const float bound = p.score_bound ? p.score_bound[head] : INFINITY;
             float m_run = -INFINITY, l_run = 0.f;      // m_run: reference exponent (log2 domain), only raised lazily
             uint32_t sreg[4][32];
             for (int j = 0; j < n_kv; ++j) {
@@ -163,6 +167,13 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + c * 32, sreg[c]);
                 tmem_ld_wait();
+                // If no score of this head can exceed the current reference by 2^15 (bound from the qk-norm gammas), the stale-reference
+                // pass below cannot overflow, the slow path cannot trigger, and S_t can be handed back to the tensor core right now.
+                const bool early = kEarlyRelease && j > 0 && __all_sync(0xffffffffu, bound - m_run < 14.0f);
+                if (early) {
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
                 FMHA_TS(2);
                 const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
                 if (valid < BKV) {
@@ -182,6 +193,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                         for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
                     m_run = sl2 * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
                 }
+                const bool pv_ready = j == 0 || mbar_try_wait(pv_done(t), (j - 1) & 1);   // polled here, its latency hides under the exps
                 FMHA_TS(3);
                 // One pass: exponentials against the (possibly stale) reference exponent.  No per-element max tracking: the only thing
                 // a stale reference can break is fp16 overflow of P, and any element >= 2^15 shows up in the block's row sum.
@@ -199,15 +211,13 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
                 const bool grow = !(lsum < kRowSumLimit);            // also catches inf / NaN
                 const bool slow = __any_sync(0xffffffffu, grow);
-                if (!slow) {                                         // common case: the scores are consumed, let the tensor core
+                if (!slow && !early) {                               // common case: the scores are consumed, let the tensor core
                     tc_fence_before();                               // overwrite S_t with block j+1 while P_t(j) is being stored
                     if (lane == 0) mbar_arrive(s_free(t));
                 }
                 FMHA_TS(4);
-                if (j > 0) {
-                    mbar_wait(pv_done(t), (j - 1) & 1, 0x62);        // PV_t(j-1) retired: P columns free, O stable
-                    tc_fence_after();
-                }
+                if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(pv_done(t), (j - 1) & 1, 0x62);   // PV_t(j-1) retired: P columns free, O stable
+                tc_fence_after();
                 if (slow) {
                     // Rare slow path (some score exceeded the reference by ~2^15): take this block's exact row max as the new
                     // reference, redo the block from the scores still in TMEM, and rescale O / l.  (Rows that did not overflow
@@ -251,7 +261,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_free(t));
+                    if (lane == 0 && !early) mbar_arrive(s_free(t));   // (early && slow cannot happen: the bound excludes overflow)
                 }
                 l_run += lsum;
                 FMHA_TS(5);

@@ -9,6 +9,7 @@ struct FmhaArgs {
     __half* out;         // [T, d_model] fp16, head h at columns [64h, 64h+64)
     int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
     float scale_log2;    // log2(e) / sqrt(head_dim)
+    const float* score_bound;  // [heads] upper bound of |score * scale_log2| (from the qk-norm gammas), or null = unknown
     long long* dbg;      // optional clock64() timeline of CTA (0,0): [iter][16] slots (tools/fmha_timeline.py), else null
 };
 
