@@ -2,6 +2,7 @@
 // sampler and the Procrustes entry points.  Host code only enqueues kernels on the caller's stream.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -48,6 +49,14 @@ void profile_mark(int kc, cudaStream_t st, bool end) {
     cudaEventRecord(e, st);
     if (!end) g_prof_open[kc] = e;
     else g_prof_events.push_back({kc, g_prof_open[kc], e});
+}
+
+// Tile width of the N=512 fp32-epilogue GEMMs (out-proj, FF2, embedding): 256 halves the A-operand re-reads and the shared-memory
+// traffic per flop; RAP_F32_BN=128 restores the two-wave 128x128 tiling for A/B measurements.
+int f32_bn() {
+    static int bn = 0;
+    if (!bn) { const char* e = getenv("RAP_F32_BN"); bn = (e && atoi(e) == 128) ? 128 : 256; }
+    return bn;
 }
 
 int num_sms() {
@@ -317,8 +326,8 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
     for (auto& kv : d->entries)
         if (!kv.second.loaded) return fail(RAP_ESTATE, "rap_dit_finalize: missing key '%s'", kv.first.c_str());
     const int L = d->L;
-    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_x, d->w_emb_x, D, 64, 64, 128));
-    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_s, d->w_emb_s, D, 128, 128, 128));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_x, d->w_emb_x, D, 64, 64, f32_bn()));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_s, d->w_emb_s, D, 128, 128, f32_bn()));
     RAP_TRY(make_tmap_f16_sw128(&d->tm_h0, d->wh0, D, D, D, 128));
     RAP_TRY(make_tmap_f16_sw128(&d->tm_h2, d->wh2, D / 2, D, D, 128));
     for (int b = 0; b < 2; ++b) { d->tm_qkv[b].resize(L); d->tm_out[b].resize(L); }
@@ -327,10 +336,10 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
         for (int b = 0; b < 2; ++b) {
             score_bound_kernel<<<1, 256>>>(d->gamma[b][l], d->score_bound + (size_t)(2 * l + b) * HEADS);
             RAP_TRY(make_tmap_f16_sw128(&d->tm_qkv[b][l], d->wqkv[b][l], 3 * D, D, D, 256));
-            RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, 128));
+            RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, f32_bn()));
         }
         RAP_TRY(make_tmap_f16_sw128(&d->tm_w1[l], d->w1[l], 2 * FF_INNER, D, D, 256));
-        RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, 128));
+        RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, f32_bn()));
     }
     d->finalized = true;
     return RAP_OK;
@@ -363,8 +372,9 @@ __global__ void sampler_timesteps_kernel(float* t, int num_steps) {   // t_i = 1
 }
 
 void build_tiles(const std::vector<int>& cu, std::vector<int4>& tiles) {
+    const int rows = fmha_rows_per_cta();
     for (size_t s = 0; s + 1 < cu.size(); ++s)
-        for (int q = cu[s]; q < cu[s + 1]; q += 256) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
+        for (int q = cu[s]; q < cu[s + 1]; q += rows) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
 }
 
 }  // namespace
@@ -455,7 +465,7 @@ extern "C" int rap_plan_set_condition(rap_plan_t* pl, const float* cond, const f
     RAP_TRY(launch_posenc_static(cond, scales, pl->scene_of_tok, feats, d->F, pl->a_s, pl->T, st));
     GemmArgs g{};
     g.M = pl->T; g.N = D; g.K = 128; g.bias = d->b_emb; g.out32 = pl->h_static; g.ld32 = D; g.table = d->anchor_emb; g.sel = anchor;
-    RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_as, d->tm_emb_s, g, st));
+    RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_as, d->tm_emb_s, g, st));
     pl->cond = cond; pl->anchor = anchor; pl->condition_set = true;
     return RAP_OK;
 }
@@ -482,7 +492,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
     {
         GemmArgs g{};
         g.M = T; g.N = D; g.K = 64; g.addend = pl->h_static; g.out32 = pl->h; g.ld32 = D;
-        RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_ax, d->tm_emb_x, g, st));
+        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ax, d->tm_emb_x, g, st));
     }
     const int row_stride = M * 2 * D;
     for (int l = 0; l < d->L; ++l) {
@@ -498,7 +508,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_tiles_part : pl->n_tiles_batch, HEADS, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
-            RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_attn16, d->tm_out[b][l], o, st));
+            RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_attn16, d->tm_out[b][l], o, st));
         }
         RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, pl->zero_rows, 0.0f, st));
         GemmArgs f1{};
@@ -507,7 +517,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
         GemmArgs f2{};
         f2.M = T; f2.N = D; f2.K = FF_INNER; f2.bias = d->b2[l]; f2.addend = pl->h; f2.out32 = pl->h; f2.ld32 = D;
         if (l == d->L - 1) { f2.out16 = pl->hh16; f2.ld16 = D; }
-        RAP_TRY(launch_gemm(EPI_F32, 128, pl->tm_ffmid, d->tm_w2[l], f2, st));
+        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ffmid, d->tm_w2[l], f2, st));
     }
     GemmArgs h0{};
     h0.M = T; h0.N = D; h0.K = D; h0.bias = d->bh0; h0.out16 = pl->y1; h0.ld16 = D;

@@ -8,6 +8,8 @@
 //   warp 1   : UMMA issuer   (S_t = Q_t K^T into TMEM cols [128t,128t+128); O_t += P_t V into cols [256+64t, ...))
 //   warps 2-5: softmax of tile 0, warps 6-9: softmax of tile 1 (thread = query row: tcgen05.ld S, online max/sum in the
 //              log2 domain, P -> smem as fp16 in the K-major SWIZZLE_128B layout UMMA reads, lazy O rescale in TMEM)
+#include <cstdlib>
+
 #include "fmha.cuh"
 #include "sm100.cuh"
 
@@ -18,25 +20,34 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;         // 16 KB: 128 rows x 128 bytes
-constexpr int KV_STAGES = 4;
-constexpr int OFF_Q = 0, OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int kThreads = 320;                    // TMA warp, UMMA warp, 2 x 4 softmax warps
+// NT = query tiles per CTA.  NT=2: one 256-row CTA per SM (K/V fetched once for both tiles, one UMMA warp ping-pongs them).
+// NT=1: one 128-row CTA, two CTAs per SM (fully independent pipelines).  Selected per launch (RAP_FMHA_NT, default 2).
+template <int NT> struct FCfg {
+    static constexpr int KV_STAGES = NT == 2 ? 4 : 3;
+    static constexpr int OFF_Q = 0, OFF_K = NT * TILE_BYTES, OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int kThreads = 64 + NT * 128;   // TMA warp, UMMA warp, NT x 4 softmax warps
+    static constexpr uint32_t TMEM_COLS = NT * 256;
+    static_assert((3 - NT) * (SMEM_BYTES + 1024) <= 233472, "shared memory budget");
+};
 // TMEM columns of query tile t: S (fp32 scores) [256t, +128), P (fp16 pairs) [256t+128, +64), O (fp32) [256t+192, +64)
-constexpr uint32_t TMEM_COLS = 512, TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
+constexpr uint32_t TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
 // Handing S back before the exponentials (possible whenever the gamma bound excludes overflow) was MEASURED slower: both query
 // tiles then run in lockstep and fight for the MUFU pipe, while the release-after-exp order staggers them naturally.
 constexpr bool kEarlyRelease = false;
 constexpr float kRowSumLimit = 32768.0f;         // a block row sum >= 2^15 means some P may leave the fp16 range: re-reference that row
-static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
 // One CTA = one 256-row query block (two 128-row tiles t=0,1) of one head; one CTA per SM.
 // The UMMA warp ping-pongs between the two tiles -- QK0, PV0, QK1, PV1 per K/V block -- so while softmax warpgroup 0
 // exponentiates block j of tile 0, the tensor core produces tile 1's scores and vice versa: the exp (MUFU) pipe, which
 // bounds head_dim-64 attention, stays busy and each K/V block is fetched once for 256 query rows.
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(FCfg<NT>::kThreads, 3 - NT)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
+    using F = FCfg<NT>;
+    constexpr int KV_STAGES = F::KV_STAGES, OFF_Q = F::OFF_Q, OFF_K = F::OFF_K, OFF_V = F::OFF_V, OFF_BAR = F::OFF_BAR;
+    constexpr uint32_t TMEM_COLS = F::TMEM_COLS;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -44,7 +55,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const int4 w = p.tiles[blockIdx.x];            // {q_row0, seg_start, seg_end, -}
     const int q0 = w.x, kv_begin = w.y, kv_end = w.z;
     const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
-    const bool two = q0 + BQ < kv_end;             // second 128-row tile has rows inside the segment
+    const bool two = NT == 2 && q0 + BQ < kv_end;  // second 128-row tile has rows inside the segment
 
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t q_full = bar;
@@ -311,18 +322,30 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
 
 }  // namespace
 
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int heads, cudaStream_t st) {
-    RAP_REQUIRE(n_tiles > 0 && heads > 0 && a.d_model == heads * HD, "fmha: bad args (tiles=%d heads=%d d=%d)", n_tiles, heads, a.d_model);
+template <int NT>
+static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int heads, cudaStream_t st) {
+    using F = FCfg<NT>;
     static bool configured = false;
     if (!configured) {
-        RAP_CUDA(cudaFuncSetAttribute(fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RAP_CUDA(cudaFuncSetAttribute(fmha_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
         configured = true;
     }
     ProfScope _ps(KC_FMHA, st);
-    fmha_kernel<<<dim3(n_tiles, heads), kThreads, SMEM_BYTES, st>>>(tm_qkv, a);
+    fmha_kernel<NT><<<dim3(n_tiles, heads), F::kThreads, F::SMEM_BYTES, st>>>(tm_qkv, a);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;
+}
+
+int fmha_rows_per_cta() {
+    static int rows = 0;
+    if (!rows) { const char* e = getenv("RAP_FMHA_NT"); rows = (e && atoi(e) == 1) ? 128 : 256; }
+    return rows;
+}
+
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int heads, cudaStream_t st) {
+    RAP_REQUIRE(n_tiles > 0 && heads > 0 && a.d_model == heads * HD, "fmha: bad args (tiles=%d heads=%d d=%d)", n_tiles, heads, a.d_model);
+    return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, a, n_tiles, heads, st) : launch_t<2>(tm_qkv, a, n_tiles, heads, st);
 }
 
 }  // namespace rap

@@ -14,6 +14,8 @@ struct FmhaArgs {
 };
 
 // tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.
+// Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM) -- tile lists must match.
+int fmha_rows_per_cta();
 int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_tiles, int heads, cudaStream_t st);
 
 }  // namespace rap

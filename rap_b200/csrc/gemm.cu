@@ -165,20 +165,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // Residual / static-embedding rows prefetched (coalesced) BEFORE waiting for the accumulator: the loads fly
                 // under this tile's MMAs.  Layout of ad[c][it]: chunk c (32 columns), rows rr0 + 4*it, 4 columns at cc*4.
                 const int col0 = n0 + half * HC;
-                float4 ad[HC / 32][8];
-#pragma unroll
-                for (int c = 0; c < HC / 32; ++c)
+                constexpr int NCH = HC / 32;                 // 32-column chunks per warp
+                auto load_addend = [&](float4 (&dst)[8], int c) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int row = row_base + it * 4 + rr0;
-                        ad[c][it] = (p.addend && row < p.M) ? *reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld32 + col0 + c * 32 + cc * 4)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        dst[it] = (p.addend && row < p.M) ? *reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld32 + col0 + c * 32 + cc * 4)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                };
+                float4 ad[2][8];                             // double-buffered: chunk c+1 streams in while chunk c is finished
+                load_addend(ad[0], 0);
+                if (NCH > 1) load_addend(ad[1], 1);
                 mbar_wait(tfull_bar(acc), acc_phase, 0x31);
                 tc_fence_after();
                 if (dbg_w) GEMM_TS(6);
 #pragma unroll
-                for (int c = 0; c < HC / 32; ++c) {
+                for (int c = 0; c < NCH; ++c) {
                     tmem_ld32(t_row + half * HC + c * 32, r);
                     tmem_ld_wait();
 #pragma unroll
@@ -191,7 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     for (int it = 0; it < 8; ++it) {
                         const int row = row_base + it * 4 + rr0;
                         const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
-                        const float4 a = ad[c][it];
+                        const float4 a = ad[c & 1][it];
                         float4 v = make_float4(__uint_as_float(u.x) + a.x + b.x, __uint_as_float(u.y) + a.y + b.y, __uint_as_float(u.z) + a.z + b.z,
                                                __uint_as_float(u.w) + a.w + b.w);
                         if (row < p.M) {
@@ -203,6 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if (p.out16) *reinterpret_cast<uint2*>(p.out16 + (size_t)row * p.ld16 + col) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
                         }
                     }
+                    if (c + 2 < NCH) load_addend(ad[c & 1], c + 2);
                     __syncwarp();
                 }
             } else {
