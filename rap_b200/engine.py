@@ -170,6 +170,8 @@ class Registrar:
     def __init__(self, state_dict: dict[str, torch.Tensor], num_layers: int, device: torch.device | str = "cuda",
                  num_steps: int = 20, rigidity_forcing: bool = False, local_feat_dim: int = 32):
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
         self.dit = DiTHandle(512, num_layers, 8, local_feat_dim)
         self.dit.load_state_dict({k: v.to(self.device) for k, v in state_dict.items()})
