@@ -227,8 +227,12 @@ def run_cuda(args) -> None:
         fm = pr.get("fmha_varlen", {"ms": float("nan"), "launches": 1})
         ach = f_attn * B / (fm["ms"] * 1e-3) / 1e12
         total_ms = sum(v["ms"] for v in pr.values())
+        # dram__bytes_read+write per fmha launch from the committed ncu --set full capture of this workload (profiles/r01_v3_ncu_summary.md):
+        # 25.4 MB read (= the 25.2 MB qkv buffer once), 0 written back (the 8.4 MB output stays in L2 for the out-projection GEMM).
+        traffic = 25.42e6 if (B == 1 and world == 1) else None
         line["roofline"] = {"bound": "tensor", "kernel": "fmha_varlen (tcgen05 QK^T/PV, hd=64)", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                            "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                            "frac": ach / pk["tflops"], "traffic": traffic, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                            "secondary_bound": "MUFU: one exp2 per score at 16/clk/SM = 1191 TFLOP/s-equivalent at 1965 MHz (tools/microbench/exp_rate.cu)",
                             "flops_per_launch": f_attn * B / max(fm["launches"], 1), "avg_launch_ms": fm["ms"] / max(fm["launches"], 1),
                             "share_of_step": fm["ms"] / total_ms if total_ms else None,
                             "path_frac": (f_gemm + f_attn) * world * B * K / t_dev / 1e12 / pk["tflops"]}
