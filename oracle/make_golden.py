@@ -99,13 +99,42 @@ def procrustes_kats(ref):
     print("procrustes_kat: done")
 
 
+SPINNET_CASES = {
+    # name: (cloud idx, n_points, n_keypoints, des_r, numpy seed)   -- "dense" fills the 512-slot patches (centre = 512th neighbour)
+    "spinnet_sparse": (0, 3000, 96, 1.5, 5),
+    "spinnet_dense": (1, 9000, 64, 4.0, 9),
+}
+
+
+def spinnet_goldens():
+    from oracle.ref_loader import load_reference_spinnet, reference_spinnet_forward
+    from rap_b200.synth import make_raw_cloud, make_spinnet_state_dict
+    M = load_reference_spinnet()
+    sd = make_spinnet_state_dict()
+    for name, (idx, n, k, des_r, seed) in SPINNET_CASES.items():
+        m = M(des_r=des_r).eval()
+        m.load_state_dict(sd, strict=True)
+        pts, kp = make_raw_cloud(idx, n, k)
+        ref = reference_spinnet_forward(m, pts[None], kp[None], des_r, seed)
+        full = int(((ref["patches"][:, -1].abs().sum(-1) == 0) & (ref["patches"][:, 0].abs().sum(-1) > 0)).sum())
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), desc=ref["desc"].numpy(), patches_head=ref["patches"][:4].numpy(),
+                            patches_checksum=np.float64(ref["patches"].double().abs().sum()), equi_checksum=np.float64(ref["equi"].double().abs().sum()))
+        print(f"{name}: desc {tuple(ref['desc'].shape)}, patches whose centre is a neighbour (not the keypoint): "
+              f"{int((ref['patches'][:, -1].abs().sum(-1) == 0).sum())}/{k}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = load_reference()
+    if sys.argv[1:] == ["spinnet"]:
+        spinnet_goldens()
+        return
     procrustes_kats(ref)
     for name in (sys.argv[1:] or CASES):
         run_case(ref, name)
+    if not sys.argv[1:]:
+        spinnet_goldens()
 
 
 if __name__ == "__main__":

@@ -169,3 +169,62 @@ def unload_reference() -> None:
     """Remove the bypass packages so `rap_b200.install()` can be tested after."""
     for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:
         del sys.modules[k]
+
+
+# ----------------------------------------------------------------------------
+# local feature extractor (MiniSpinNet): reference dataset_process/utils/spinnet/*
+# ----------------------------------------------------------------------------
+def _ball_query_shim(p1, p2, lengths1=None, lengths2=None, K=500, radius=0.2, return_nn=True):
+    """pytorch3d.ops.ball_query (0.7.8, pinned only in reference scripts/install.sh:16 -- absent offline, restated):
+    for every query of p1 the FIRST K points of p2 (in index order) with squared distance < radius^2;
+    idx padded with -1, dists (squared) and nn padded with 0."""
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    d2 = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)                   # (B,P1,P2)
+    inside = d2 < radius * radius
+    rank = torch.cumsum(inside.long(), dim=-1) - 1                                # position among the in-radius points
+    take = inside & (rank < K)
+    idx = torch.full((B, P1, K), -1, dtype=torch.long, device=p1.device)
+    dists = torch.zeros(B, P1, K, dtype=p1.dtype, device=p1.device)
+    b, i, j = take.nonzero(as_tuple=True)
+    idx[b, i, rank[b, i, j]] = j
+    dists[b, i, rank[b, i, j]] = d2[b, i, j]
+    nn_pts = None
+    if return_nn:
+        nn_pts = torch.zeros(B, P1, K, p2.shape[2], dtype=p2.dtype, device=p2.device)
+        nn_pts[b, i, rank[b, i, j]] = p2[b, j]
+    return dists, idx, nn_pts
+
+
+def load_reference_spinnet():
+    """The reference's own `MiniSpinNet` class executed verbatim (CPU): package-bypass for `dataset_process`
+    (its `utils/__init__.py` imports open3d/h5py tooling) + a `pytorch3d.ops.ball_query` shim.  The hard-coded `.cuda()`
+    at patch_embedder.py:176 is neutralised by the caller (see `reference_spinnet_forward`)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    root = os.path.join(REFERENCE_ROOT, "dataset_process")
+    for name, path in (("dataset_process", root), ("dataset_process.utils", os.path.join(root, "utils"))):
+        if name not in sys.modules or not getattr(sys.modules[name], "_rap_bypass", False):
+            m = types.ModuleType(name)
+            m.__path__ = [path]
+            m._rap_bypass = True
+            sys.modules[name] = m
+    if "pytorch3d" not in sys.modules:
+        p3 = types.ModuleType("pytorch3d"); p3.__path__ = []
+        ops = types.ModuleType("pytorch3d.ops"); ops.ball_query = _ball_query_shim
+        sys.modules["pytorch3d"], sys.modules["pytorch3d.ops"] = p3, ops
+    return importlib.import_module("dataset_process.utils.spinnet.patch_embedder").MiniSpinNet
+
+
+def reference_spinnet_forward(model, pts, kpts, des_r, numpy_seed):
+    """Runs the reference MiniSpinNet.forward on CPU with numpy seeded (the point shuffle at patch_embedder.py:99 uses the global
+    numpy RNG) and `.cuda()` turned into a no-op for the duration of the call."""
+    import numpy as np
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        np.random.seed(numpy_seed)
+        with torch.no_grad():
+            return model(pts=pts, kpts=kpts, des_r=des_r, is_aligned_to_global_z=True)
+    finally:
+        torch.Tensor.cuda = orig

@@ -231,3 +231,47 @@ def make_batch(num_scenes: int, views: int, pts_per_view: int | list[int], max_p
         anchor_indices=torch.from_numpy(np.concatenate([s.anchor for s in scenes])),
         points_per_part=ppp, cu_seqlens_batch=cu_b, cu_seqlens_part=cu_p, x_1=x1,
         gt=torch.from_numpy(np.concatenate([s.gt for s in scenes])))
+
+
+# ----------------------------------------------------------------------------
+# MiniSpinNet (local feature extractor) weights
+# ----------------------------------------------------------------------------
+def spinnet_state_dict_spec() -> list[tuple[str, tuple[int, ...], str]]:
+    """(key, shape, kind) of the reference MiniSpinNet.state_dict() (dataset_process/utils/spinnet/patch_embedder.py:31-47,
+    patchnet.py:68-84), verified against the reference class.  `Desc.`-prefixed in BUFFER-X style checkpoints."""
+    def bn(prefix, c, affine):
+        out = [(prefix + "weight", (c,), "ln_w"), (prefix + "bias", (c,), "linear_b")] if affine else []
+        return out + [(prefix + "running_mean", (c,), "bn_mean"), (prefix + "running_var", (c,), "bn_var"), (prefix + "num_batches_tracked", (), "count")]
+    spec = [("pnt_layer.0.weight", (16, 3, 1, 1), "conv_w"), ("pnt_layer.0.bias", (16,), "linear_b")] + bn("pnt_layer.1.", 16, True)
+    spec += [("pool_layer.0.weight", (16, 32, 1, 1), "conv_w"), ("pool_layer.0.bias", (16,), "linear_b")] + bn("pool_layer.1.", 16, True)
+    spec += [("pool_layer.3.weight", (1, 16, 1, 1), "conv_w"), ("pool_layer.3.bias", (1,), "pool_b")] + bn("pool_layer.4.", 1, True)
+    spec += [("conv_net.ops.0.weight", (64, 16, 3, 3, 3), "conv_w"), ("conv_net.ops.0.bias", (64,), "linear_b")] + bn("conv_net.ops.1.", 64, False)
+    chans = [(3, 64, 64), (6, 128, 64), (9, 128, 128), (12, 64, 128), (15, 64, 64), (18, 32, 64)]
+    for i, co, ci in chans:
+        spec += [(f"conv_net.ops.{i}.weight", (co, ci, 3, 3), "conv_w"), (f"conv_net.ops.{i}.bias", (co,), "linear_b")] + bn(f"conv_net.ops.{i + 1}.", co, False)
+    spec += [("conv_net.ops.21.weight", (32, 32, 3, 3), "conv_w"), ("conv_net.ops.21.bias", (32,), "linear_b")]
+    return spec
+
+
+def make_spinnet_state_dict(seed: int = 0) -> dict[str, torch.Tensor]:
+    """Seeded MiniSpinNet weights with non-trivial BatchNorm running statistics (eval mode uses them)."""
+    out = {}
+    for key, shape, kind in spinnet_state_dict_spec():
+        g = torch.Generator(device="cpu")
+        g.manual_seed((seed * 1000003 + zlib.crc32(("spinnet." + key).encode())) & 0x7FFFFFFF)
+        if kind == "count":
+            out[key] = torch.tensor(100, dtype=torch.long)
+            continue
+        u = torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        out[key] = {"conv_w": u * (1.5 / fan_in ** 0.5), "linear_b": u * 0.05, "pool_b": u * 0.05 + 0.5, "ln_w": 1.0 + 0.1 * u,
+                    "bn_mean": u * 0.1, "bn_var": 0.6 + 0.3 * u}[kind].contiguous()
+    return out
+
+
+def make_raw_cloud(idx: int, n_points: int, n_keypoints: int, seed: int = 77):
+    """A raw (un-normalised, metric) view cloud + keypoints drawn from it, for the extractor."""
+    rng = np.random.default_rng(seed + idx)
+    pts = _surface_cloud(rng, n_points).astype(np.float32)
+    kp = pts[rng.choice(n_points, n_keypoints, replace=False)]
+    return torch.from_numpy(pts), torch.from_numpy(kp)
