@@ -78,6 +78,24 @@ int rap_procrustes_rigidify(const float* prediction, const float* condition, con
 int rap_plan_fit(rap_plan_t* plan, const float* source, const float* target, float* rotations, float* translations, void* stream);
 int rap_plan_rigidify(rap_plan_t* plan, const float* prediction, const float* condition, float* out, void* stream);
 
+/* ---- local feature extractor: replaces dataset_process.extract_sample_features.FeatureExtractor / MiniSpinNet.forward
+ * (dataset_process/extract_sample_features.py:151-220, dataset_process/utils/spinnet/patch_embedder.py:49-91) ------------------
+ * Weights: the MiniSpinNet state_dict (the `Desc.`-stripped keys, fp32 device tensors; num_batches_tracked is not needed).
+ * extract: points (n_points,3) f32, perm int32 [n_points] = the shuffle the reference draws with np.random.choice (NULL = identity),
+ * keypoints (n_keypoints,3) f32, des_r = descriptor radius -> desc (n_keypoints,32) f32, L2-normalised. */
+typedef struct rap_spinnet rap_spinnet_t;
+int rap_spinnet_create(rap_spinnet_t** out);
+void rap_spinnet_destroy(rap_spinnet_t* h);
+int rap_spinnet_num_keys(const rap_spinnet_t* h);
+const char* rap_spinnet_key(const rap_spinnet_t* h, int index, int64_t* numel_out);
+int rap_spinnet_load_weight(rap_spinnet_t* h, const char* key, const float* src, int64_t numel, void* stream);
+int rap_spinnet_finalize(rap_spinnet_t* h);
+int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_points, const int32_t* perm, const float* keypoints, int n_keypoints,
+                        float des_r, float* desc_out, void* stream);
+
+int rap_test_spinnet_patches(const float* points, int n_points, const int32_t* perm, const float* keypoints, int n_keypoints, float des_r,
+                             float* patches_out, void* stream);
+
 /* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
 int rap_kabsch_host(const double* H9, double* R9);
 

@@ -47,6 +47,14 @@ PROTOTYPES = {
     "rap_procrustes_rigidify": (C.c_int, [_f32p, _f32p, _vp, C.c_int, _f32p, _f32p, C.c_float, C.c_float, _vp]),
     "rap_plan_fit": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _vp]),
     "rap_plan_rigidify": (C.c_int, [_vp, _f32p, _f32p, _f32p, _vp]),
+    "rap_spinnet_create": (C.c_int, [C.POINTER(_vp)]),
+    "rap_spinnet_destroy": (None, [_vp]),
+    "rap_spinnet_num_keys": (C.c_int, [_vp]),
+    "rap_spinnet_key": (C.c_char_p, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "rap_spinnet_load_weight": (C.c_int, [_vp, C.c_char_p, _f32p, C.c_int64, _vp]),
+    "rap_spinnet_finalize": (C.c_int, [_vp]),
+    "rap_spinnet_extract": (C.c_int, [_vp, _f32p, C.c_int, _vp, _f32p, C.c_int, C.c_float, _f32p, _vp]),
+    "rap_test_spinnet_patches": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.c_int, C.c_float, _f32p, _vp]),
     "rap_kabsch_host": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rap_launch_count": (C.c_int64, []),
     "rap_profile_begin": (C.c_int, []),

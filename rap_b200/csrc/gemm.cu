@@ -229,10 +229,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col + i), b1 = *reinterpret_cast<const float4*>(p.bias + col + 32 + i);
-                            pk[i / 2] = pack_half2(silu(__uint_as_float(r[i]) + b0.x), silu(__uint_as_float(r[i + 1]) + b0.y));
-                            pk[i / 2 + 1] = pack_half2(silu(__uint_as_float(r[i + 2]) + b0.z), silu(__uint_as_float(r[i + 3]) + b0.w));
-                            pk[16 + i / 2] = pack_half2(silu(__uint_as_float(r2[i]) + b1.x), silu(__uint_as_float(r2[i + 1]) + b1.y));
-                            pk[16 + i / 2 + 1] = pack_half2(silu(__uint_as_float(r2[i + 2]) + b1.z), silu(__uint_as_float(r2[i + 3]) + b1.w));
+                            float v[8] = {__uint_as_float(r[i]) + b0.x, __uint_as_float(r[i + 1]) + b0.y, __uint_as_float(r[i + 2]) + b0.z, __uint_as_float(r[i + 3]) + b0.w,
+                                          __uint_as_float(r2[i]) + b1.x, __uint_as_float(r2[i + 1]) + b1.y, __uint_as_float(r2[i + 2]) + b1.z, __uint_as_float(r2[i + 3]) + b1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = p.act ? fmaxf(v[j], 0.f) : silu(v[j]);
+                            pk[i / 2] = pack_half2(v[0], v[1]);
+                            pk[i / 2 + 1] = pack_half2(v[2], v[3]);
+                            pk[16 + i / 2] = pack_half2(v[4], v[5]);
+                            pk[16 + i / 2 + 1] = pack_half2(v[6], v[7]);
                         }
                     } else if constexpr (EPI == EPI_QKV) {
                         // One 64-column head per round.  section 0/1 = q/k (RMS-normalised), 2 = v.

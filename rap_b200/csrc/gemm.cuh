@@ -10,7 +10,7 @@ namespace rap {
 
 enum GemmEpi : int {
     EPI_F32 = 0,     // out32 = acc (+bias[col]) (+addend[row,col]) (+table[sel[row]][col]); optional fp16 shadow
-    EPI_F16_SILU,    // out16 = silu(acc + bias[col])
+    EPI_F16_SILU,    // out16 = act(acc + bias[col]), act = SiLU (args.act = 0) or ReLU (args.act = 1)
     EPI_QKV,         // per-head RMS norm * gamma * sqrt(hd) on q,k; v passthrough; out16 [M,N]
     EPI_GEGLU,       // tile cols [0,BN/2)=h, [BN/2,BN)=g (weights pre-interleaved); out16[M,N/2] = h*gelu(g)
 };
@@ -25,6 +25,7 @@ struct GemmArgs {
     const float* table;       // [2, N] row-select table (anchor embedding) or null
     const unsigned char* sel; // [M] row selector for `table`
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
+    int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
 };
 

@@ -2,7 +2,7 @@
 # Runs the GPU test files one process each (a trapped kernel poisons its CUDA context) with per-file timeouts.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-for f in tests/test_gpu_kernels.py tests/test_gpu_parity.py; do
+for f in tests/test_gpu_kernels.py tests/test_gpu_parity.py tests/test_gpu_spinnet.py; do
   n=$(basename $f .py)
   timeout 600 python -m pytest $f -q -m gpu -s --timeout 300 > gpurun_out/$n.log 2>&1
   echo "$n exit=$?" | tee -a gpurun_out/summary.txt
