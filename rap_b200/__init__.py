@@ -36,3 +36,11 @@ def install(package: str = "rectified_point_flow") -> None:
         setattr(parent, name, mod)
     pc = importlib.import_module("rap_b200.rectified_point_flow.utils.point_clouds")
     sys.modules.setdefault(f"{package}.utils.point_clouds", pc)
+
+
+def install_extractor(module: str = "dataset_process.extract_sample_features") -> None:
+    """Replace the reference's `FeatureExtractor` class (MiniSpinNet wrapper) by the CUDA extractor, leaving the rest of the
+    module (SampleProcessor, FPS, outlier removal, CLI) untouched.  No-op-safe: raises ImportError if the reference module is absent."""
+    ref = importlib.import_module(module)
+    mine = importlib.import_module("rap_b200.dataset_process.extract_sample_features")
+    ref.FeatureExtractor = mine.FeatureExtractor
