@@ -59,6 +59,12 @@ int f32_bn() {
     return bn;
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_NO_PDL"); v = (e && atoi(e) == 1) ? 0 : 1; }
+    return v == 1;
+}
+
 int num_sms() {
     static int n = 0;
     if (!n) {

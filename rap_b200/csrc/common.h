@@ -43,6 +43,20 @@ int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint6
                         uint32_t box_rows);
 
 int num_sms();
+
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the stream is still draining; it
+// must call pdl_wait() before reading or writing global memory.  RAP_NO_PDL=1 falls back to plain stream order (A/B measurements).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 void note_launch(int n = 1);   // counts kernels launched by this library (rap_launch_count)
 
 // Optional per-kernel-class timing (rap_profile_begin/_end): CUDA events recorded on the launching stream

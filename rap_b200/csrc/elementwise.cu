@@ -2,6 +2,7 @@
 // AdaLN conditioning MLP, head tail + Euler update, weight packing.  All fp32 math, fp16 only as
 // the GEMM operand format.
 #include "kernels.cuh"
+#include "sm100.cuh"
 
 namespace rap { extern __device__ unsigned int g_dev_error; }
 
@@ -44,6 +45,8 @@ __global__ void posenc_static_kernel(const float* __restrict__ cond, const float
 }
 
 __global__ void posenc_x_kernel(const float* __restrict__ xin, __half* __restrict__ out, int T) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = idx >> 6, e = idx & 63;
     if (row >= T) return;
@@ -59,6 +62,8 @@ __global__ void posenc_x_kernel(const float* __restrict__ xin, __half* __restric
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ h, __half* __restrict__ out, int T, const float* __restrict__ mul,
                    const float* __restrict__ add, int row_stride, const int* row_of_tok, float one_plus) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     const float4* src = reinterpret_cast<const float4*>(h + (size_t)row * D);
@@ -137,6 +142,8 @@ ada_linear_kernel(const __half* __restrict__ W, const float* __restrict__ b, con
 __global__ void __launch_bounds__(256)
 head_final_kernel(const __half* __restrict__ y2, const float* __restrict__ W4, int T, float* __restrict__ v_out,
                   float* __restrict__ x_t, float t, float dt, float* __restrict__ x0hat_out, float* __restrict__ xt_traj) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     const uint4 raw = reinterpret_cast<const uint4*>(y2 + (size_t)row * 256)[lane];
@@ -200,16 +207,14 @@ int launch_posenc_static(const float* cond, const float* scales, const int* scen
 }
 int launch_posenc_x(const float* x, __half* out, int T, cudaStream_t st) {
     ProfScope _ps(KC_POSENC, st);
-    posenc_x_kernel<<<ceil_div(T * 64, 256), 256, 0, st>>>(x, out, T);
-    RAP_CUDA(cudaGetLastError());
+    RAP_CUDA(launch_pdl(posenc_x_kernel, dim3(ceil_div(T * 64, 256)), dim3(256), 0, st, x, out, T));
     note_launch();
     return RAP_OK;
 }
 int launch_ln_modulate(const float* h, __half* out, int T, const float* mul, const float* add, int row_stride,
                        const int* row_of_tok, float one_plus, cudaStream_t st) {
     ProfScope _ps(KC_LN, st);
-    ln_modulate_kernel<<<ceil_div(T, 8), 256, 0, st>>>(h, out, T, mul, add, row_stride, row_of_tok, one_plus);
-    RAP_CUDA(cudaGetLastError());
+    RAP_CUDA(launch_pdl(ln_modulate_kernel, dim3(ceil_div(T, 8)), dim3(256), 0, st, h, out, T, mul, add, row_stride, row_of_tok, one_plus));
     note_launch();
     return RAP_OK;
 }
@@ -234,8 +239,7 @@ int launch_ada_linear(const __half* W, const float* b, const float* in, int in_h
 int launch_head_final(const __half* y2, const float* W4, int T, float* v_out, float* x_t, float t, float dt,
                       float* x0hat_out, float* xt_traj, cudaStream_t st) {
     ProfScope _ps(KC_HEAD, st);
-    head_final_kernel<<<ceil_div(T, 8), 256, 0, st>>>(y2, W4, T, v_out, x_t, t, dt, x0hat_out, xt_traj);
-    RAP_CUDA(cudaGetLastError());
+    RAP_CUDA(launch_pdl(head_final_kernel, dim3(ceil_div(T, 8)), dim3(256), 0, st, y2, W4, T, v_out, x_t, t, dt, x0hat_out, xt_traj));
     note_launch();
     return RAP_OK;
 }

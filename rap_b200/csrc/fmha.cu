@@ -50,9 +50,10 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     constexpr uint32_t TMEM_COLS = F::TMEM_COLS;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
-    const int4 w = p.tiles[blockIdx.x];            // {q_row0, seg_start, seg_end, -}
+    const int4 w = p.tiles[blockIdx.x];            // {q_row0, seg_start, seg_end, -}  (plan data, not produced by the previous kernel)
     const int q0 = w.x, kv_begin = w.y, kv_end = w.z;
     const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
     const bool two = NT == 2 && q0 + BQ < kv_end;  // second 128-row tile has rows inside the segment
@@ -84,6 +85,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 200);
 
     const int col_q = head * HD, col_k = p.d_model + head * HD, col_v = 2 * p.d_model + head * HD;
+    pdl_wait();                                    // qkv comes from the previous kernel
 
     if (warp == 0) {
         const bool leader = elect_one();
@@ -331,8 +333,7 @@ static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, i
         configured = true;
     }
     ProfScope _ps(KC_FMHA, st);
-    fmha_kernel<NT><<<dim3(n_tiles, heads), F::kThreads, F::SMEM_BYTES, st>>>(tm_qkv, a);
-    RAP_CUDA(cudaGetLastError());
+    RAP_CUDA(launch_pdl(fmha_kernel<NT>, dim3(n_tiles, heads), dim3(F::kThreads), F::SMEM_BYTES, st, tm_qkv, a));
     note_launch();
     return RAP_OK;
 }

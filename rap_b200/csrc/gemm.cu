@@ -64,6 +64,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
     float* gamma_s = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_blocks = p.K / BK;
     const int num_tiles = m_tiles * n_tiles;
@@ -83,6 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    pdl_wait();                                   // operands / residual come from the previous kernel
 
     const bool dbg_cta = p.dbg && blockIdx.x == 0;
     int dbg_tile = 0;
@@ -324,8 +326,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope _ps(EPI == EPI_F32 ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
-    gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, a);
-    RAP_CUDA(cudaGetLastError());
+    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, tmA, tmB, a));
     note_launch();
     return RAP_OK;
 }

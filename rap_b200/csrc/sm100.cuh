@@ -25,6 +25,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every hot kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it signals `launch_dependents` at once, runs
+// its prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream drains, and only then
+// blocks in `pdl_wait()` (= full completion + memory visibility of the previous kernel) before touching any global data.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
