@@ -74,6 +74,13 @@ int rap_procrustes_fit(const float* source, const float* target, const int32_t* 
  * rigidify_prediction_with_procrustes is w_rigid=1, mix=NULL; sampler.py:60 is w_rigid=1-t+dt, w_mix=t-dt. */
 int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_seqlens_part, int n_parts,
                             float* out, const float* mix, float w_rigid, float w_mix, void* stream);
+/* Generation selection (modeling.py:456-547, eval/metrics.py:511-622): per slot sum of squared residuals |R src + t - tgt|^2, either
+ * fused with the fit (one launch per trajectory step instead of fit_transformations + compute_rigidity_rmse host loops) or for a
+ * given (R,t).  sse (slots) must be zero-initialised by the caller. */
+int rap_procrustes_fit_sse(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot, int n_parts,
+                           float* rotations, float* translations, float* sse, void* stream);
+int rap_rigid_sse(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot, int n_parts,
+                  const float* rotations, const float* translations, float* sse, void* stream);
 /* Plan-bound convenience wrappers using the plan's own part table. */
 int rap_plan_fit(rap_plan_t* plan, const float* source, const float* target, float* rotations, float* translations, void* stream);
 int rap_plan_rigidify(rap_plan_t* plan, const float* prediction, const float* condition, float* out, void* stream);

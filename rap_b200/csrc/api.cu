@@ -591,6 +591,18 @@ extern "C" int rap_procrustes_rigidify(const float* prediction, const float* con
     return launch_procrustes(condition, prediction, cu_part, nullptr, n_parts, nullptr, nullptr, out, nullptr, mix, w_rigid, w_mix,
                              static_cast<cudaStream_t>(stream));
 }
+extern "C" int rap_procrustes_fit_sse(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
+                                      float* rotations, float* translations, float* sse, void* stream) {
+    RAP_REQUIRE(source && target && cu_part && rotations && translations && sse && n_parts >= 0, "rap_procrustes_fit_sse: bad argument");
+    return launch_procrustes(source, target, cu_part, slot, n_parts, rotations, translations, nullptr, nullptr, nullptr, 0.f, 0.f,
+                             static_cast<cudaStream_t>(stream), sse);
+}
+extern "C" int rap_rigid_sse(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
+                             const float* rotations, const float* translations, float* sse, void* stream) {
+    RAP_REQUIRE(source && target && cu_part && rotations && translations && sse && n_parts >= 0, "rap_rigid_sse: bad argument");
+    return launch_procrustes(source, target, cu_part, slot, n_parts, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
+                             static_cast<cudaStream_t>(stream), sse, rotations, translations);
+}
 extern "C" int rap_plan_fit(rap_plan_t* pl, const float* source, const float* target, float* rotations, float* translations, void* stream) {
     RAP_REQUIRE(pl, "rap_plan_fit: NULL plan");
     return rap_procrustes_fit(source, target, pl->cu_part, pl->slot, pl->VP, rotations, translations, stream);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads)
 procrustes_kernel(const float* __restrict__ src, const float* __restrict__ tgt, const int* __restrict__ cu_part,
                   const int* __restrict__ slot, float* __restrict__ R_out, float* __restrict__ t_out,
                   float* __restrict__ apply_out, float* __restrict__ apply_out2, const float* __restrict__ mix,
-                  float w_rigid, float w_mix) {
+                  float w_rigid, float w_mix, float* __restrict__ sse_out, const float* __restrict__ R_in, const float* __restrict__ t_in) {
     __shared__ double red[(kThreads / 32) * 9];
     __shared__ double res[9];
     __shared__ float Rt[12];
@@ -111,7 +111,12 @@ procrustes_kernel(const float* __restrict__ src, const float* __restrict__ tgt, 
     if (n <= 0) return;
     const float* S = src + (size_t)s * 3;
     const float* G = tgt + (size_t)s * 3;
-
+    const int sl_io = slot ? slot[part] : part;
+    if (R_in) {                                   // residual of a GIVEN transform (eval/metrics.py:511-622): skip the fit
+        if (threadIdx.x < 9) Rt[threadIdx.x] = R_in[(size_t)sl_io * 9 + threadIdx.x];
+        else if (threadIdx.x < 12) Rt[threadIdx.x] = t_in[(size_t)sl_io * 3 + threadIdx.x - 9];
+        __syncthreads();
+    } else {
     double m[6] = {0, 0, 0, 0, 0, 0};
     for (int i = threadIdx.x; i < n; i += kThreads) {
         m[0] += S[3 * i]; m[1] += S[3 * i + 1]; m[2] += S[3 * i + 2];
@@ -148,6 +153,20 @@ procrustes_kernel(const float* __restrict__ src, const float* __restrict__ tgt, 
         }
     }
     __syncthreads();
+    }
+    if (sse_out) {                                // sum of squared residuals |R s + t - g|^2 of the part (fp64 accumulation)
+        double acc[1] = {0.0};
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const float x = S[3 * i], y = S[3 * i + 1], z = S[3 * i + 2];
+            const float d0 = Rt[0] * x + Rt[1] * y + Rt[2] * z + Rt[9] - G[3 * i];
+            const float d1 = Rt[3] * x + Rt[4] * y + Rt[5] * z + Rt[10] - G[3 * i + 1];
+            const float d2 = Rt[6] * x + Rt[7] * y + Rt[8] * z + Rt[11] - G[3 * i + 2];
+            acc[0] += (double)(d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        __syncthreads();
+        block_reduce<1>(acc, red, res);
+        if (threadIdx.x == 0) sse_out[sl_io] = (float)res[0];
+    }
     if (apply_out) {
         const float r0 = Rt[0], r1 = Rt[1], r2 = Rt[2], r3 = Rt[3], r4 = Rt[4], r5 = Rt[5], r6 = Rt[6], r7 = Rt[7], r8 = Rt[8];
         const float t0 = Rt[9], t1 = Rt[10], t2 = Rt[11];
@@ -170,10 +189,10 @@ void kabsch_host(const double* H, double* R) { kabsch_from_covariance(H, R); }
 
 int launch_procrustes(const float* src, const float* tgt, const int* cu_part, const int* slot, int n_parts,
                       float* R_out, float* t_out, float* apply_out, float* apply_out2, const float* mix,
-                      float w_rigid, float w_mix, cudaStream_t st) {
+                      float w_rigid, float w_mix, cudaStream_t st, float* sse_out, const float* R_in, const float* t_in) {
     if (n_parts <= 0) return RAP_OK;
     ProfScope _ps(KC_PROCRUSTES, st);
-    procrustes_kernel<<<n_parts, kThreads, 0, st>>>(src, tgt, cu_part, slot, R_out, t_out, apply_out, apply_out2, mix, w_rigid, w_mix);
+    procrustes_kernel<<<n_parts, kThreads, 0, st>>>(src, tgt, cu_part, slot, R_out, t_out, apply_out, apply_out2, mix, w_rigid, w_mix, sse_out, R_in, t_in);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;

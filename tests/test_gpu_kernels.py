@@ -175,3 +175,56 @@ def test_procrustes_planted_full_size(rap):
     R, t = procrustes.fit_transformations(src, tgt, ppp, torch.tensor([0, 8192], device="cuda", dtype=torch.int32))
     _sync_check(rap)
     assert (R[0] - q).abs().max() < 1e-5 and (t[0] - tt).abs().max() < 1e-5
+
+
+def test_rigidity_rmse_matches_reference_formula(rap):
+    """compute_rigidity_rmse (eval/metrics.py:511-622) restated in torch vs the fused kernel, both averaging modes, padded slots."""
+    from rap_b200.rectified_point_flow import procrustes
+    from rap_b200.rectified_point_flow.eval.metrics import compute_rigidity_rmse, fit_and_rigidity_sse
+    g = torch.Generator("cuda").manual_seed(21)
+    ppp = torch.tensor([[300, 0, 212], [0, 0, 0], [128, 64, 8]], device="cuda")
+    T = int(ppp.sum())
+    src = torch.randn(T, 3, device="cuda", generator=g)
+    tgt = src + 0.05 * torch.randn(T, 3, device="cuda", generator=g)
+    cu_b = torch.tensor([0, 512, 512, 712], device="cuda", dtype=torch.int32)
+    R, t = procrustes.fit_transformations(src, tgt, ppp, cu_b)
+    scales = torch.tensor([2.0, 3.0, 0.5], device="cuda")
+    R2, t2, sse = fit_and_rigidity_sse(src, tgt, ppp)
+    assert torch.equal(R2, R) and torch.equal(t2, t)
+    for per_part in (False, True):
+        got = compute_rigidity_rmse(src, tgt, R, t, ppp, cu_b, scales, average_per_part=per_part)
+        want, off = [], 0
+        for b in range(3):
+            errs = []
+            for p in range(3):
+                n = int(ppp[b, p])
+                if n == 0: continue
+                e = ((src[off:off + n] @ R[b, p].t() + t[b, p] - tgt[off:off + n]) ** 2).sum(1)
+                errs.append(e); off += n
+            if not errs: want.append(float("inf"))
+            elif per_part: want.append(float(torch.stack([x.mean().sqrt() for x in errs]).mean()) * float(scales[b]))
+            else: want.append(float(torch.cat(errs).mean().sqrt()) * float(scales[b]))
+        _sync_check(rap)
+        assert got[1] == float("inf")
+        assert abs(got[0].item() - want[0]) < 1e-5 and abs(got[2].item() - want[2]) < 1e-5
+
+
+def test_trajectory_rigidity_selection(rap):
+    """modeling.py:462-518: per-step fit + RMSE averaged over steps, argmin over generations; vs the per-step mirror calls."""
+    from rap_b200.rectified_point_flow import procrustes
+    from rap_b200.rectified_point_flow.eval.metrics import compute_rigidity_rmse, select_generation, trajectory_rigidity_rmse
+    g = torch.Generator("cuda").manual_seed(5)
+    ppp = torch.tensor([[100, 156, 0], [64, 0, 192]], device="cuda")
+    cu_b = torch.tensor([0, 256, 512], device="cuda", dtype=torch.int32)
+    cond = torch.randn(512, 3, device="cuda", generator=g)
+    scales = torch.tensor([1.5, 0.7], device="cuda")
+    scores = []
+    for noise in (0.2, 0.02, 0.1):
+        traj = cond[None] + noise * torch.randn(4, 512, 3, device="cuda", generator=g)
+        got = trajectory_rigidity_rmse(cond, traj, ppp, scales)
+        want = torch.stack([compute_rigidity_rmse(cond, traj[i], *procrustes.fit_transformations(cond, traj[i], ppp, cu_b), ppp, cu_b, scales)
+                            for i in range(4)]).mean(0)
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+        scores.append(got)
+    _sync_check(rap)
+    assert select_generation(torch.stack(scores)).tolist() == [1, 1]
