@@ -210,18 +210,25 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 FMHA_TS(3);
                 // One pass: exponentials against the (possibly stale) reference exponent.  No per-element max tracking: the only thing
                 // a stale reference can break is fp16 overflow of P, and any element >= 2^15 shows up in the block's row sum.
-                float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                f32x2 ls[4] = {0ull, 0ull, 0ull, 0ull};                // packed pairs: FFMA2 / FADD2 halve the issue slots around the MUFUs
+                const f32x2 sl2x2 = pack2(sl2, sl2), nmx2 = pack2(-m_run, -m_run);
                 uint32_t preg[64];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float a = ex2f(fmaf(__uint_as_float(sreg[c][i]), sl2, -m_run));
-                        const float b = ex2f(fmaf(__uint_as_float(sreg[c][i + 1]), sl2, -m_run));
-                        ls[(i >> 1) & 7] += a + b;
+                        float ua, ub;
+                        unpack2(ffma2(pack2(__uint_as_float(sreg[c][i]), __uint_as_float(sreg[c][i + 1])), sl2x2, nmx2), ua, ub);
+                        const float a = ex2f(ua), b = ex2f(ub);
+                        ls[(i >> 1) & 3] = fadd2(ls[(i >> 1) & 3], pack2(a, b));
                         preg[c * 16 + i / 2] = pack_half2(a, b);
                     }
-                float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+                float lsum;
+                {
+                    float s0, s1;
+                    unpack2(fadd2(fadd2(ls[0], ls[1]), fadd2(ls[2], ls[3])), s0, s1);
+                    lsum = s0 + s1;
+                }
                 const bool grow = !(lsum < kRowSumLimit);            // also catches inf / NaN
                 const bool slow = __any_sync(0xffffffffu, grow);
                 if (!slow && !early) {                               // common case: the scores are consumed, let the tensor core
