@@ -103,6 +103,27 @@ int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_points, con
 int rap_test_spinnet_patches(const float* points, int n_points, const int32_t* perm, const float* keypoints, int n_keypoints, float des_r,
                              float* patches_out, void* stream);
 
+/* ---- keypoint selection in front of the extractor ------------------------------------------------------------
+ * All pointers are device pointers unless noted; the calls synchronise the stream (they return counts to the host).
+ *
+ * rap_voxel_downsample  replaces dataset_utils.voxel_down_sample_torch (dataset_process/utils/dataset_utils.py:279-322): one index per
+ *                       occupied voxel (point nearest the voxel centre in 1000 quantised steps, ties to the lowest index), ordered by
+ *                       the reference's flattened voxel id.  indices_out: capacity n (int64, device); count_out: host.
+ * rap_voxel_coverage    replaces calculate_voxel_coverage (dataset_process/utils/point_sampling_utils.py:11-31): occupied voxel count of
+ *                       floor(points / voxel_size) evaluated in the array's own precision (is_f64 selects double input).
+ * rap_fps_batched       replaces pytorch3d sample_farthest_points(points (N,P,3), lengths, K, random_start_point) as called by
+ *                       apply_batched_fps (point_sampling_utils.py:263-309); start_idx holds the per-cloud start indices (the host draws
+ *                       them with torch.randint like the reference).  indices_out (N,max_k) int64, -1 padded; sampled_out (N,max_k,3)
+ *                       optional.  One thread-block cluster per cloud, points register-resident: at most rap_fps_capacity() per cloud.
+ * rap_statistical_outliers replaces open3d PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio) as called at
+ *                       dataset_process/extract_sample_features.py:360-413: keep_out (n) uint8 mask (device), n_keep_out host. */
+int rap_voxel_downsample(const float* points, int n, float voxel_size, int64_t* indices_out, int* count_out, void* stream);
+int rap_voxel_coverage(const void* points, int n, int is_f64, double voxel_size, int* count_out, void* stream);
+int rap_fps_capacity(void);
+int rap_fps_batched(const float* points, int n_clouds, int max_points, const int32_t* lengths, const int32_t* k, const int32_t* start_idx,
+                    int max_k, int64_t* indices_out, float* sampled_out, void* stream);
+int rap_statistical_outliers(const float* points, int n, int nb_neighbors, double std_ratio, uint8_t* keep_out, int* n_keep_out, void* stream);
+
 /* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
 int rap_kabsch_host(const double* H9, double* R9);
 

@@ -123,6 +123,57 @@ def spinnet_goldens():
               f"{int((ref['patches'][:, -1].abs().sum(-1) == 0).sum())}/{k}")
 
 
+PREPROC_VOXEL_CASES = {
+    # name: (cloud idx, n_points, voxel_size, snap)   -- snap=True rounds coordinates onto voxel faces (floor / tie edge cases)
+    "a": (2, 20000, 0.8, False), "b": (3, 6000, 0.25, False), "c": (4, 3000, 1.0, True), "d": (5, 50000, 0.4, False),
+}
+
+
+def preproc_cloud(idx, n, snap=False):
+    from rap_b200.synth import make_raw_cloud
+    pts, _ = make_raw_cloud(idx, n, 8)
+    pts = pts.numpy().astype(np.float32)
+    return (np.round(pts * 2) / 2).astype(np.float32) if snap else pts
+
+
+def preproc_goldens():
+    """Reference functions run verbatim: voxel_down_sample_torch (CPU) and the keypoint budget rules (numpy, seeded)."""
+    import importlib
+    import types
+    from oracle.ref_loader import load_reference_spinnet
+    load_reference_spinnet()                                      # dataset_process package bypass + pytorch3d shim
+    sys.modules["pytorch3d.ops"].sample_farthest_points = None    # imported by name in point_sampling_utils, never called here
+    sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    io = types.ModuleType("dataset_process.utils.io_utils"); io.get_dataset_name = lambda *a, **k: ""
+    sys.modules["dataset_process.utils.io_utils"] = io
+    du = importlib.import_module("dataset_process.utils.dataset_utils")
+    psu = importlib.import_module("dataset_process.utils.point_sampling_utils")
+    out = {}
+    for name, (idx, n, vs, snap) in PREPROC_VOXEL_CASES.items():
+        out[f"voxel_{name}"] = du.voxel_down_sample_torch(torch.from_numpy(preproc_cloud(idx, n, snap)), vs).numpy()
+        out[f"coverage_{name}"] = np.int64(psu.calculate_voxel_coverage(preproc_cloud(idx, n, snap), 4 * vs))
+        out[f"coverage64_{name}"] = np.int64(psu.calculate_voxel_coverage(preproc_cloud(idx, n, snap).astype(np.float64), 4 * vs))
+    rng = np.random.default_rng(11)
+    cases, pc, sc = [], [], []
+    import logging
+    logging.disable(logging.WARNING)
+    for trial in range(40):
+        n = int(rng.integers(1, 9))
+        pts, cov = rng.integers(1, 5000, size=n), rng.integers(0, 800, size=n)
+        num, mn = int(rng.integers(10, 6000)), int(rng.integers(1, 400))
+        np.random.seed(trial); a = psu._allocate_by_point_count_logic(pts.copy(), num, mn)
+        np.random.seed(trial); b = psu._allocate_by_spatial_coverage_logic(cov.copy(), pts.copy(), num, mn)
+        row = np.zeros(8 * 4 + 3, np.int64)
+        row[:3] = n, num, mn
+        row[3:3 + n], row[11:11 + n], row[19:19 + n], row[27:27 + n] = pts, cov, a, b
+        cases.append(row)
+    out["alloc_cases"] = np.stack(cases)
+    parts = [preproc_cloud(6, 4000), preproc_cloud(7, 900), np.zeros((0, 3), np.float32)]
+    out["adaptive_counts"] = np.array(psu.calculate_adaptive_sample_count_per_part(parts, 2.0, 0.5, 100, 1500), np.int64)
+    np.savez_compressed(os.path.join(OUT, "preproc.npz"), **out)
+    print("preproc:", {k: (v.shape if hasattr(v, "shape") and v.shape else int(v)) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -130,11 +181,15 @@ def main():
     if sys.argv[1:] == ["spinnet"]:
         spinnet_goldens()
         return
+    if sys.argv[1:] == ["preproc"]:
+        preproc_goldens()
+        return
     procrustes_kats(ref)
     for name in (sys.argv[1:] or CASES):
         run_case(ref, name)
     if not sys.argv[1:]:
         spinnet_goldens()
+        preproc_goldens()
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librap_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "fmha.cu", "elementwise.cu", "procrustes.cu", "spinnet.cu"]
+SOURCES = ["api.cu", "gemm.cu", "fmha.cu", "elementwise.cu", "procrustes.cu", "spinnet.cu", "preproc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-rdc=true", "-Xptxas", "-v"]
 

@@ -84,7 +84,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    pdl_wait();                                   // operands / residual come from the previous kernel
+    // Programmatic dependent launch: only the A operand, the residual and the outputs depend on the previous kernel.  The weight
+    // (B) tiles of the first pipeline stages are requested BEFORE griddepcontrol.wait, so their fetch latency hides under the
+    // previous kernel's tail; the UMMA warp never touches global memory and does not wait at all.
 
     const bool dbg_cta = p.dbg && blockIdx.x == 0;
     int dbg_tile = 0;
@@ -93,16 +95,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------ TMA producer (warp converged, one elected lane issues)
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
+        const int pre = (blockIdx.x < num_tiles) ? min(C::STAGES, k_blocks) : 0;   // stages whose B tile is in flight before the wait
+        if (leader) {
+            const int n0 = (blockIdx.x % n_tiles) * BN;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(full_bar(kb), C::STAGE_BYTES);
+                tma_load_2d(smem_base + kb * C::STAGE_BYTES + A_STAGE_BYTES, &tmB, full_bar(kb), kb * BK, n0);
+            }
+        }
+        pdl_wait();
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            const bool first = tile == (int)blockIdx.x;
             GEMM_TS(0);
             for (int kb = 0; kb < k_blocks; ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
+                const bool b_done = first && kb < pre;          // this stage's barrier is armed and its B tile already requested
+                if (!b_done) mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
                 if (leader) {
-                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    if (!b_done) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+                    if (!b_done) tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -139,6 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
         // ------------------------------------------------------------ epilogue: 8 warps.  TMEM lane quarter = warp % 4
         // (hardware rule), column half = (warp - 2) / 4, so two warps share a quarter and split the tile's columns.
+        pdl_wait();                                      // residual reads and output writes order after the previous kernel
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int HC = BN / 2;                       // accumulator columns per warp

@@ -1,2 +1,3 @@
-"""Mirror of the reference's `dataset_process.extract_sample_features.FeatureExtractor` on the sm_100a extractor kernels."""
-from .extract_sample_features import FeatureExtractor  # noqa: F401
+"""Mirror of the reference's `dataset_process` modules on the hot path: the local feature extractor and the keypoint selection in
+front of it (voxel down-sampling, outlier removal, keypoint budgets, batched FPS)."""
+from .extract_sample_features import FeatureExtractor, SampleProcessor, remove_statistical_outlier  # noqa: F401

@@ -89,3 +89,109 @@ class FeatureExtractor:
         if getattr(self, "_h", None):
             lib.rap_spinnet_destroy(self._h)
             self._h = None
+
+
+def remove_statistical_outlier(points: np.ndarray, nb_neighbors: int, std_ratio: float) -> np.ndarray:
+    """Inlier indices of open3d's `PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio)` (mean distance to the
+    nb_neighbors nearest points, the point itself included, below mean + std_ratio * std over the cloud) on the CUDA KNN kernel."""
+    pts = torch.from_numpy(np.ascontiguousarray(points)).to("cuda", torch.float32).contiguous()
+    keep = torch.empty(pts.shape[0], dtype=torch.uint8, device=pts.device)
+    n_keep = C.c_int(0)
+    check(lib.rap_statistical_outliers(ptr(pts), pts.shape[0], int(nb_neighbors), float(std_ratio), ptr(keep), C.byref(n_keep), stream_ptr()),
+          "rap_statistical_outliers")
+    return torch.nonzero(keep).flatten().cpu().numpy()
+
+
+class SampleProcessor:
+    """`dataset_process.extract_sample_features.SampleProcessor` (reference :223-620) with every stage on the GPU: statistical
+    outlier removal -> pre-FPS cap -> keypoint budget per part -> batched FPS -> descriptors with the ORIGINAL part as context.
+    Same constructor arguments, same numpy / torch RNG call sequence, same return value (one dict per part)."""
+
+    def __init__(self, feature_extractor: FeatureExtractor, num_points: int = 5000, skip_point_sampling: bool = False,
+                 remove_outliers: bool = True, outlier_nb_neighbors: int = 20, outlier_std_ratio: float = 2.0, min_points_per_part: int = 100,
+                 max_points_per_part: int = 10000, global_seed: int = 42, allocation_method: str = "point_count", voxel_size: float = 1.0,
+                 voxel_ratio: float = 0.1):
+        if allocation_method not in ("point_count", "spatial_coverage", "voxel_adaptive"):
+            raise ValueError(f"allocation_method must be 'point_count', 'spatial_coverage', or 'voxel_adaptive', got: {allocation_method}")
+        self.feature_extractor, self.num_points, self.skip_point_sampling = feature_extractor, num_points, skip_point_sampling
+        self.remove_outliers, self.outlier_nb_neighbors, self.outlier_std_ratio = remove_outliers, outlier_nb_neighbors, outlier_std_ratio
+        self.min_points_per_part, self.max_points_per_part, self.global_seed = min_points_per_part, max_points_per_part, global_seed
+        self.allocation_method, self.voxel_size, self.voxel_ratio = allocation_method, voxel_size, voxel_ratio
+
+    def _set_sample_seed(self, sample_idx: int = 0):
+        seed = self.global_seed + sample_idx * 1000
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+
+    def select_keypoints(self, parts_points, parts_normals=None):
+        """Stages 2-3 of process_sample (reference :359-575): returns (fps_parts, target_per_part, indices (n_parts, max K) tensor)."""
+        from .utils.point_sampling_utils import allocate_fps_points, apply_batched_fps, calculate_adaptive_sample_count_per_part
+        fps_parts, fps_normals = list(parts_points), list(parts_normals or [None] * len(parts_points))
+        if self.remove_outliers:
+            for i, part in enumerate(fps_parts):
+                if len(part) < self.outlier_nb_neighbors:
+                    continue
+                inliers = remove_statistical_outlier(part, self.outlier_nb_neighbors, self.outlier_std_ratio)
+                if len(inliers):
+                    fps_parts[i] = part[inliers]
+                    fps_normals[i] = fps_normals[i][inliers] if fps_normals[i] is not None else None
+        if self.max_points_per_part is not None:
+            cap = 20 * self.max_points_per_part
+            for i, part in enumerate(fps_parts):
+                if len(part) > cap:
+                    keep = np.random.choice(len(part), cap, replace=False)
+                    fps_parts[i] = part[keep].copy()
+                    fps_normals[i] = fps_normals[i][keep].copy() if fps_normals[i] is not None else None
+        if self.allocation_method == "voxel_adaptive":
+            counts = calculate_adaptive_sample_count_per_part(fps_parts, self.voxel_size, self.voxel_ratio, self.min_points_per_part,
+                                                              self.max_points_per_part)
+            target = allocate_fps_points(fps_parts, self.allocation_method, self.num_points, self.min_points_per_part, self.voxel_size,
+                                         self.voxel_ratio, total_sample_points=counts)
+        elif self.allocation_method == "spatial_coverage":
+            target = allocate_fps_points(fps_parts, self.allocation_method, self.num_points, self.min_points_per_part, self.voxel_size,
+                                         self.voxel_ratio)
+        else:
+            target = allocate_fps_points(np.array([len(p) for p in fps_parts]), self.allocation_method, self.num_points,
+                                         self.min_points_per_part, self.voxel_size, self.voxel_ratio)
+        rows = [i for i, k in enumerate(target) if k != 0]
+        if not rows:
+            return fps_parts, fps_normals, target, rows, None, None
+        lengths = [len(fps_parts[i]) for i in rows]
+        ks = [min(int(target[i]), len(fps_parts[i])) for i in rows]
+        batch = torch.zeros(len(rows), max(lengths), 3)
+        for r, i in enumerate(rows):
+            batch[r, :lengths[r]] = torch.from_numpy(fps_parts[i]).float()
+        sampled, indices = apply_batched_fps(batch, torch.tensor(lengths, dtype=torch.int64), torch.tensor(ks, dtype=torch.int64),
+                                             self.global_seed, self.feature_extractor.device)
+        return fps_parts, fps_normals, target, rows, sampled, indices
+
+    def process_sample(self, parts_points, parts_normals=None):
+        if not parts_points:
+            return []
+        normals_in = parts_normals or [None] * len(parts_points)
+        kept = [(p.copy(), n.copy() if n is not None else None) for p, n in zip(parts_points, normals_in) if len(p)]
+        if not kept:
+            return {"sampled_points": np.array([]), "sampled_normals": None, "features": np.array([])}
+        originals, normals = [p for p, _ in kept], [n for _, n in kept]
+        dev = self.feature_extractor.device
+        if self.skip_point_sampling:
+            out = []
+            for pts, nrm in zip(originals, normals):
+                t = torch.from_numpy(pts).float().to(dev)
+                feats = self.feature_extractor.extract_features(points=t, keypoints=t)["features"]
+                out.append({"sampled_points": pts, "sampled_normals": nrm, "features": feats.cpu().numpy()})
+            return out
+        fps_parts, fps_normals, _, rows, sampled, indices = self.select_keypoints(originals, normals)
+        if sampled is None:
+            return []
+        out = []
+        for r, kp in enumerate(sampled):
+            if kp.numel() == 0:
+                continue
+            # NB the reference pairs sampled part r with originals[r] (extract_sample_features.py:593), i.e. positions, not `rows`
+            feats = self.feature_extractor.extract_features(points=torch.from_numpy(originals[r]).float().to(dev), keypoints=kp)["features"]
+            nrm = fps_normals[rows[r]]
+            sel = indices[r][:kp.shape[0]].cpu().numpy()
+            out.append({"sampled_points": kp.cpu().numpy(), "sampled_normals": nrm[sel] if nrm is not None else None,
+                        "features": feats.cpu().numpy()})
+        return out

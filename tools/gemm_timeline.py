@@ -24,5 +24,7 @@ def run(name, epi, bn, M, N, K):
         print(f"  tile{t}: prod [{r[0]-t0},{r[1]-t0}]  mma wait_acc {r[3]-r[2]} issue_span {r[4]-r[3]} (start {r[2]-t0})  epi start {r[5]-t0} acc_ready {r[6]-t0} done {r[7]-t0} (epi work {r[7]-r[6]})")
 run("qkv", 2, 256, 8192, 1536, 512)
 run("geglu", 3, 256, 8192, 4096, 512)
-run("outproj f32", 0, 128, 8192, 512, 512)
-run("ff2 f32", 0, 128, 8192, 512, 2048)
+run("outproj f32", 0, 256, 8192, 512, 512)
+run("ff2 f32", 0, 256, 8192, 512, 2048)
+run("outproj f32 bn128", 0, 128, 8192, 512, 512)
+run("ff2 f32 bn128", 0, 128, 8192, 512, 2048)
