@@ -124,6 +124,10 @@ int rap_fps_batched(const float* points, int n_clouds, int max_points, const int
                     int max_k, int64_t* indices_out, float* sampled_out, void* stream);
 int rap_statistical_outliers(const float* points, int n, int nb_neighbors, double std_ratio, uint8_t* keep_out, int* n_keep_out, void* stream);
 
+/* Pose application (demo.py:1330-1340, open3d PointCloud.transform): out = R p + t over a full-resolution cloud,
+ * fp32 or fp64 points (device), the affine 4x4 row-major in HOST memory.  In-place (out == points) is allowed. */
+int rap_apply_transform(const void* points, long long n, int is_f64, const double* transform_4x4_host, void* out, void* stream);
+
 /* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
 int rap_kabsch_host(const double* H9, double* R9);
 

@@ -174,6 +174,61 @@ def preproc_goldens():
     print("preproc:", {k: (v.shape if hasattr(v, "shape") and v.shape else int(v)) for k, v in out.items()})
 
 
+def eval_case(seed=3):
+    """Seeded inputs shared by the generator and the tests: B=3 objects (one empty), P=4 part slots.  Empty slots trail: the reference's
+    split_parts (utils/point_clouds.py:47) compacts empty parts away, so its [b][p] indexing only holds for trailing padding."""
+    g = torch.Generator().manual_seed(seed)
+    ppp = torch.tensor([[120, 200, 64, 0], [0, 0, 0, 0], [90, 300, 0, 0]])
+    T = int(ppp.sum())
+
+    def rot(n):
+        q, _ = torch.linalg.qr(torch.randn(n, 3, 3, generator=g))
+        return q * torch.sign(torch.det(q))[:, None, None]
+    d = {"points_per_part": ppp, "cond": torch.randn(T, 3, generator=g), "scales": torch.tensor([2.5, 1.0, 0.4]),
+         "rotations": rot(12).reshape(3, 4, 3, 3), "translations": torch.randn(3, 4, 3, generator=g),
+         "rotations_pred": rot(12).reshape(3, 4, 3, 3), "translations_pred": torch.randn(3, 4, 3, generator=g),
+         "global_rotation": rot(1)[0], "global_translation": torch.randn(3, generator=g) * 10,
+         "cu_seqlens_batch": torch.tensor([0, 384, 384, 774], dtype=torch.int32)}
+    off, pred = 0, []
+    for b in range(3):
+        for p_ in range(4):
+            n = int(ppp[b, p_])
+            x = d["cond"][off:off + n]
+            pred.append(x @ d["rotations_pred"][b, p_].T + d["translations_pred"][b, p_] + 0.03 * torch.randn(n, 3, generator=g))
+            off += n
+    d["pred"] = torch.cat(pred)
+    return d
+
+
+def eval_goldens():
+    """`compute_rigidity_rmse` (eval/metrics.py:511-622) and the `*_transform.txt` writer (eval/evaluator.py:383-497) run verbatim."""
+    import tempfile
+    from pathlib import Path
+    from oracle.ref_loader import load_reference_eval
+    ref = load_reference_eval()
+    d = eval_case()
+    out = {}
+    for per_part in (False, True):
+        out[f"rigidity_rmse_{int(per_part)}"] = ref.metrics.compute_rigidity_rmse(
+            d["cond"], d["pred"], d["rotations_pred"], d["translations_pred"], d["points_per_part"], d["cu_seqlens_batch"], d["scales"],
+            average_per_part=per_part).numpy()
+    out["rigidity_rmse_noscale"] = ref.metrics.compute_rigidity_rmse(d["cond"], d["pred"], d["rotations_pred"], d["translations_pred"],
+                                                                     d["points_per_part"], d["cu_seqlens_batch"]).numpy()
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, (gi, with_global) in {"plain": (0, False), "global": ("selected", True)}.items():
+            sub = Path(tmp) / tag
+            sub.mkdir()
+            for b in (0, 2):
+                ref.evaluator.Evaluator._save_transformation_files(
+                    None, d, b, sub, "synth", 7 + b, generation_idx=gi, rotations_pred=d["rotations_pred"], translations_pred=d["translations_pred"],
+                    global_rotation=d["global_rotation"] if with_global else None, global_translation=d["global_translation"] if with_global else None)
+            files = sorted(sub.iterdir())
+            out[f"files_{tag}"] = np.array([f.name for f in files])
+            out[f"text_{tag}"] = np.array([f.read_text() for f in files])
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **out)
+    print("eval:", out["rigidity_rmse_0"], out["rigidity_rmse_1"], list(out["files_global"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -184,12 +239,16 @@ def main():
     if sys.argv[1:] == ["preproc"]:
         preproc_goldens()
         return
+    if sys.argv[1:] == ["eval"]:
+        eval_goldens()
+        return
     procrustes_kats(ref)
     for name in (sys.argv[1:] or CASES):
         run_case(ref, name)
     if not sys.argv[1:]:
         spinnet_goldens()
         preproc_goldens()
+        eval_goldens()
 
 
 if __name__ == "__main__":

@@ -165,6 +165,40 @@ def load_reference():
     return ns
 
 
+def load_reference_eval():
+    """The reference's own `eval.metrics` (for `compute_rigidity_rmse`) and `eval.evaluator.Evaluator` (for the `*_transform.txt` writer,
+    `_save_transformation_files`) executed verbatim.  lightning / open3d / pytorch3d / the renderer are only named at import time on
+    these two code paths, so empty stand-ins are enough."""
+    load_reference()
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+        else:
+            for k, v in attrs.items():
+                if not hasattr(sys.modules[name], k):
+                    setattr(sys.modules[name], k, v)
+    stub("lightning", LightningModule=object)
+    stub("open3d")
+    stub("pytorch3d")
+    stub("pytorch3d.loss")
+    stub("pytorch3d.loss.chamfer", chamfer_distance=None)
+    stub("pytorch3d.ops", iterative_closest_point=None)
+    stub(_PKG + ".utils.render", part_ids_to_colors=None)
+    root = os.path.join(REFERENCE_ROOT, _PKG, "eval")
+    if _PKG + ".eval" not in sys.modules:
+        m = types.ModuleType(_PKG + ".eval")
+        m.__path__ = [root]
+        sys.modules[_PKG + ".eval"] = m
+    ns = types.SimpleNamespace()
+    ns.metrics = importlib.import_module(_PKG + ".eval.metrics")
+    ns.evaluator = importlib.import_module(_PKG + ".eval.evaluator")
+    return ns
+
+
 def unload_reference() -> None:
     """Remove the bypass packages so `rap_b200.install()` can be tested after."""
     for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:

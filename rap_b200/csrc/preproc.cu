@@ -316,9 +316,38 @@ __global__ void threshold_kernel(const double* __restrict__ avg, int n, double t
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
 }
 
+// ------------------------------------------------------------------------------------------------ pose application
+// out = R p + t for every point of a full-resolution cloud (demo.py:1338-1340, open3d PointCloud.transform): 24 B/point of traffic.
+struct Rigid { double r[9], t[3]; };
+template <typename T>
+__global__ void apply_transform_kernel(const T* __restrict__ in, T* __restrict__ out, long long n, Rigid m) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+        out[3 * i] = (T)((T)m.r[0] * x + (T)m.r[1] * y + (T)m.r[2] * z + (T)m.t[0]);
+        out[3 * i + 1] = (T)((T)m.r[3] * x + (T)m.r[4] * y + (T)m.r[5] * z + (T)m.t[1]);
+        out[3 * i + 2] = (T)((T)m.r[6] * x + (T)m.r[7] * y + (T)m.r[8] * z + (T)m.t[2]);
+    }
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
+extern "C" int rap_apply_transform(const void* points, long long n, int is_f64, const double* transform_4x4_host, void* out, void* stream) {
+    RAP_REQUIRE(points && out && transform_4x4_host && n >= 0, "rap_apply_transform: bad argument");
+    const double* T = transform_4x4_host;
+    RAP_REQUIRE(T[12] == 0.0 && T[13] == 0.0 && T[14] == 0.0 && T[15] == 1.0, "rap_apply_transform: not an affine 4x4 (last row must be 0 0 0 1)");
+    if (n == 0) return RAP_OK;
+    Rigid m;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) m.r[r * 3 + c] = T[r * 4 + c]; m.t[r] = T[r * 4 + 3]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 8ll * num_sms());
+    if (is_f64) apply_transform_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(points), static_cast<double*>(out), n, m);
+    else apply_transform_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(points), static_cast<float*>(out), n, m);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+
 extern "C" int rap_voxel_downsample(const float* points, int n, float voxel_size, int64_t* indices_out, int* count_out, void* stream) {
     RAP_REQUIRE(points && indices_out && count_out && n > 0 && voxel_size > 0.f, "rap_voxel_downsample: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

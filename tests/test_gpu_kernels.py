@@ -228,3 +228,37 @@ def test_trajectory_rigidity_selection(rap):
         scores.append(got)
     _sync_check(rap)
     assert select_generation(torch.stack(scores)).tolist() == [1, 1]
+
+
+def test_rigidity_rmse_matches_reference_golden(rap, golden_dir):
+    """compute_rigidity_rmse run verbatim from the reference (oracle/make_golden.py eval) vs the fused kernel, incl. an empty object."""
+    import os
+    from oracle.make_golden import eval_case
+    from rap_b200.rectified_point_flow.eval import compute_rigidity_rmse
+    g = np.load(os.path.join(golden_dir, "eval.npz"))
+    d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in eval_case().items()}
+    args = (d["cond"], d["pred"], d["rotations_pred"], d["translations_pred"], d["points_per_part"], d["cu_seqlens_batch"])
+    for per_part in (False, True):
+        got = compute_rigidity_rmse(*args, d["scales"], average_per_part=per_part).cpu().numpy()
+        _sync_check(rap)
+        np.testing.assert_allclose(got, g[f"rigidity_rmse_{int(per_part)}"], rtol=2e-5)
+    np.testing.assert_allclose(compute_rigidity_rmse(*args).cpu().numpy(), g["rigidity_rmse_noscale"], rtol=2e-5)
+
+
+def test_apply_transform_full_resolution(rap):
+    """demo.py:1330-1340: pose relative to the first scan applied to a full-resolution cloud; fp64 and fp32 clouds, numpy and tensor."""
+    from rap_b200.rectified_point_flow.eval import apply_transform, relative_to_reference
+    rng = np.random.default_rng(1)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    T = np.eye(4); T[:3, :3] = q * np.sign(np.linalg.det(q)); T[:3, 3] = [10.5, -3.25, 0.125]
+    T = relative_to_reference([np.eye(4), T])[1]
+    pts = rng.standard_normal((2_000_003, 3)) * 50
+    want = pts @ T[:3, :3].T + T[:3, 3]
+    got64 = apply_transform(pts, T)
+    assert got64.dtype == np.float64 and np.abs(got64 - want).max() < 1e-11
+    got32 = apply_transform(torch.from_numpy(pts.astype(np.float32)).cuda(), T)
+    _sync_check(rap)
+    assert got32.is_cuda and got32.dtype == torch.float32 and np.abs(got32.cpu().numpy() - want).max() < 5e-5
+    with pytest.raises(RuntimeError):
+        bad = T.copy(); bad[3, 0] = 0.1
+        apply_transform(pts[:10], bad)
