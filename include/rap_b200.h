@@ -128,6 +128,15 @@ int rap_statistical_outliers(const float* points, int n, int nb_neighbors, doubl
  * fp32 or fp64 points (device), the affine 4x4 row-major in HOST memory.  In-place (out == points) is allowed. */
 int rap_apply_transform(const void* points, long long n, int is_f64, const double* transform_4x4_host, void* out, void* stream);
 
+/* Timing aid (tools/fmha_split_sweep.py): mean duration of `iters` back-to-back attention launches on the default stream. */
+int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out, int iters, float* ms_per_launch);
+
+/* Host-only helper (no GPU): the attention work list of one launch -- (query block, head) units, the units of the last partially filled
+ * wave cut along the key axis so every SM finishes together; 8 int32 per item {q_row0, seg_start, seg_end, head, kv_lo, kv_hi, slot,
+ * piece | n_pieces << 8}.  Returns the number of items (items_out may be NULL to query it). */
+int rap_fmha_schedule(const int32_t* cu_seqlens_host, int n_segments, int heads, int force_split, int32_t* items_out, int capacity,
+                      int* n_slots_out, int* max_pieces_out);
+
 /* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
 int rap_kabsch_host(const double* H9, double* R9);
 
@@ -145,7 +154,7 @@ const char* rap_profile_class_name(int kernel_class);
 int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
                   const float* addend, float* out32, void* out16, const float* gamma, void* dbg, void* stream);
 /* dbg: optional device buffer of n_kv_blocks*16 int64 receiving a clock64() timeline of CTA (0,0), or NULL. */
-int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out_f16,
+int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, int force_split, void* out_f16,
                   void* dbg, void* stream);
 
 int rap_test_ln_modulate(const float* h, void* out_f16, int T, const float* mul, const float* add, int row_stride,

@@ -62,6 +62,8 @@ PROTOTYPES = {
     "rap_fps_batched": (C.c_int, [_f32p, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _f32p, _vp]),
     "rap_statistical_outliers": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), _vp]),
     "rap_apply_transform": (C.c_int, [_vp, C.c_longlong, C.c_int, C.POINTER(C.c_double), _vp, _vp]),
+    "rap_bench_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int, C.POINTER(C.c_float)]),
+    "rap_fmha_schedule": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rap_test_spinnet_patches": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.c_int, C.c_float, _f32p, _vp]),
     "rap_kabsch_host": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rap_launch_count": (C.c_int64, []),
@@ -72,7 +74,7 @@ PROTOTYPES = {
     "rap_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _f32p, _f32p, _vp, _f32p, _vp, _vp]),
     "rap_test_ln_modulate": (C.c_int, [_f32p, _vp, C.c_int, _f32p, _f32p, C.c_int, _vp, C.c_float, _vp]),
     "rap_debug_read": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
-    "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, _vp, _vp]),
+    "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in PROTOTYPES.items():
     _fn = getattr(lib, _name)           # AttributeError here = header/library mismatch

@@ -355,11 +355,13 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
 struct rap_plan {
     rap_dit* dit = nullptr;
     int T = 0, B = 0, P = 0, VP = 0, n_cap = 0;
-    int n_tiles_part = 0, n_tiles_batch = 0;
+    int n_items_part = 0, n_items_batch = 0, fmha_pieces_part = 0, fmha_pieces_batch = 0;
     char* ws = nullptr;
     // layout
     int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr, *zero_rows = nullptr;
-    int4 *tiles_part = nullptr, *tiles_batch = nullptr;
+    FmhaItem *items_part = nullptr, *items_batch = nullptr;
+    float* fmha_ws = nullptr;      // partial rows of split attention units (shared by the two attention launches of a layer)
+    int* fmha_counters = nullptr;
     // activations
     float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
     __half *x16 = nullptr, *attn16 = nullptr, *qkv = nullptr, *ffmid = nullptr, *a_s = nullptr, *a_x = nullptr, *hh16 = nullptr, *y1 = nullptr, *y2 = nullptr;
@@ -375,12 +377,6 @@ namespace {
 __global__ void sampler_timesteps_kernel(float* t, int num_steps) {   // t_i = 1 - i * (1/num_steps), rounded like float(python double)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < num_steps) t[i] = (float)(1.0 - (double)i * (1.0 / (double)num_steps));
-}
-
-void build_tiles(const std::vector<int>& cu, std::vector<int4>& tiles) {
-    const int rows = fmha_rows_per_cta();
-    for (size_t s = 0; s + 1 < cu.size(); ++s)
-        for (int q = cu[s]; q < cu[s + 1]; q += rows) tiles.push_back(make_int4(q, cu[s], cu[s + 1], 0));
 }
 
 }  // namespace
@@ -405,19 +401,21 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
         RAP_REQUIRE(sum == cu_b[b + 1] - cu_b[b], "rap_plan_create: sum(points_per_part[%d])=%d != scene length %d", b, sum, cu_b[b + 1] - cu_b[b]);
         for (int i = cu_b[b]; i < cu_b[b + 1]; ++i) scene_of_tok[i] = b;
     }
-    std::vector<int4> tp, tb;
-    build_tiles(cu_part, tp);
-    build_tiles(cu_batch, tb);
+    const FmhaSchedule sp = build_fmha_schedule(cu_part, HEADS), sb = build_fmha_schedule(cu_batch, HEADS);
+    const std::vector<FmhaItem>&tp = sp.items, &tb = sb.items;
+    const size_t fmha_ws_floats = std::max(sp.workspace_floats(), sb.workspace_floats());
+    const size_t fmha_slots = (size_t)std::max(sp.n_slots, sb.n_slots);
 
     rap_plan* pl = new rap_plan();
     pl->dit = dit; pl->T = T; pl->B = n_scenes; pl->P = max_parts; pl->VP = (int)slot.size();
     pl->n_cap = std::max(std::max(max_timesteps, n_scenes), 1);
-    pl->n_tiles_part = (int)tp.size(); pl->n_tiles_batch = (int)tb.size();
+    pl->n_items_part = (int)tp.size(); pl->n_items_batch = (int)tb.size(); pl->fmha_pieces_part = sp.max_pieces; pl->fmha_pieces_batch = sb.max_pieces;
     const int M = dit->M;
     const size_t Tp = (size_t)((T + 127) / 128) * 128;     // padded rows so tail tiles stay in-bounds for plain loads/stores
     size_t bytes = 0;
     auto need = [&](size_t n) { bytes = ((bytes + 255) & ~size_t(255)) + n; };
-    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(4 * (size_t)T); need(16 * tp.size()); need(16 * tb.size());
+    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(4 * (size_t)T); need(sizeof(FmhaItem) * tp.size()); need(sizeof(FmhaItem) * tb.size());
+    need(4 * fmha_ws_floats); need(4 * fmha_slots + 4);
     need(4 * Tp * D); need(4 * Tp * D); need(4 * Tp * 3); need(4 * (size_t)pl->n_cap);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * 3 * D); need(2 * Tp * FF_INNER); need(2 * Tp * 128); need(2 * Tp * 64);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * (D / 2));
@@ -427,7 +425,8 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     cudaMemset(pl->ws, 0, bytes);
     Slab s; s.base = pl->ws; s.size = bytes;
     pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T); pl->zero_rows = s.take<int>(T);
-    pl->tiles_part = s.take<int4>(tp.size()); pl->tiles_batch = s.take<int4>(tb.size());
+    pl->items_part = s.take<FmhaItem>(tp.size()); pl->items_batch = s.take<FmhaItem>(tb.size());
+    pl->fmha_ws = s.take<float>(fmha_ws_floats); pl->fmha_counters = s.take<int>(fmha_slots + 1);
     pl->h = s.take<float>(Tp * D); pl->h_static = s.take<float>(Tp * D); pl->x_t = s.take<float>(Tp * 3); pl->tbuf = s.take<float>(pl->n_cap);
     pl->x16 = s.take<__half>(Tp * D); pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
     pl->a_s = s.take<__half>(Tp * 128); pl->a_x = s.take<__half>(Tp * 64);
@@ -439,8 +438,8 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     cudaError_t e = up(pl->cu_part, cu_part.data(), 4 * cu_part.size());
     if (e == cudaSuccess) e = up(pl->slot, slot.data(), 4 * slot.size());
     if (e == cudaSuccess) e = up(pl->scene_of_tok, scene_of_tok.data(), 4 * (size_t)T);
-    if (e == cudaSuccess) e = up(pl->tiles_part, tp.data(), 16 * tp.size());
-    if (e == cudaSuccess) e = up(pl->tiles_batch, tb.data(), 16 * tb.size());
+    if (e == cudaSuccess) e = up(pl->items_part, tp.data(), sizeof(FmhaItem) * tp.size());
+    if (e == cudaSuccess) e = up(pl->items_batch, tb.data(), sizeof(FmhaItem) * tb.size());
     int rc = e == cudaSuccess ? RAP_OK : fail(RAP_ECUDA, "rap_plan_create: upload failed: %s", cudaGetErrorString(e));
     // A-operand tensor maps (rows = T so out-of-range rows of the last tile are zero-filled by TMA)
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_x16, pl->x16, T, D, D, 128);
@@ -509,9 +508,10 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
             FmhaArgs f{};
-            f.tiles = b == 0 ? pl->tiles_part : pl->tiles_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
+            f.items = b == 0 ? pl->items_part : pl->items_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;
+            f.ws_pieces = b == 0 ? pl->fmha_pieces_part : pl->fmha_pieces_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
             f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
-            RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_tiles_part : pl->n_tiles_batch, HEADS, st));
+            RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
             RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_attn16, d->tm_out[b][l], o, st));
@@ -624,23 +624,74 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, void* dbg, void* stream) {
+// Host-only: the attention work list (whole units + key-split pieces of the last wave) for segments cu[0..n]; 8 ints per item
+// {q_row0, seg_start, seg_end, head, kv_lo, kv_hi, slot, piece | n_pieces << 8}.  Returns the item count (negative on error).
+extern "C" int rap_fmha_schedule(const int32_t* cu_host, int n_segments, int heads, int force_split, int32_t* items_out, int capacity, int* n_slots_out,
+                                 int* max_pieces_out) {
+    RAP_REQUIRE(cu_host && n_segments >= 1 && heads >= 1, "rap_fmha_schedule: bad argument");
+    const FmhaSchedule sch = build_fmha_schedule(std::vector<int>(cu_host, cu_host + n_segments + 1), heads, force_split != 0);
+    if (n_slots_out) *n_slots_out = sch.n_slots;
+    if (max_pieces_out) *max_pieces_out = sch.max_pieces;
+    if (items_out) {
+        RAP_REQUIRE((size_t)capacity >= sch.items.size(), "rap_fmha_schedule: capacity %d < %zu items", capacity, sch.items.size());
+        memcpy(items_out, sch.items.data(), sizeof(FmhaItem) * sch.items.size());
+    }
+    return (int)sch.items.size();
+}
+
+// Timing aid: `iters` back-to-back launches of one attention call between two events (schedule built once, like a plan does).
+extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, float* ms_per_launch) {
+    RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch, "rap_bench_fmha: bad argument");
+    const FmhaSchedule sch = build_fmha_schedule(std::vector<int>(cu_host, cu_host + n_segments + 1), heads);
+    FmhaItem* dt = nullptr; float* ws = nullptr; int* counters = nullptr;
+    RAP_CUDA(cudaMalloc(&dt, sizeof(FmhaItem) * sch.items.size()));
+    RAP_CUDA(cudaMemcpy(dt, sch.items.data(), sizeof(FmhaItem) * sch.items.size(), cudaMemcpyHostToDevice));
+    RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
+    RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
+    RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
+    CUtensorMap tm;
+    RAP_TRY(make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128));
+    FmhaArgs f{};
+    f.items = dt; f.ws = ws; f.counters = counters; f.ws_pieces = sch.max_pieces;
+    f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = RAP_OK;
+    for (int i = 0; i < 3 && !rc; ++i) rc = launch_fmha(tm, f, (int)sch.items.size(), nullptr);
+    cudaEventRecord(e0, nullptr);
+    for (int i = 0; i < iters && !rc; ++i) rc = launch_fmha(tm, f, (int)sch.items.size(), nullptr);
+    cudaEventRecord(e1, nullptr);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(ms_per_launch, e0, e1);
+    *ms_per_launch /= iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dt); cudaFree(ws); cudaFree(counters);
+    return rc;
+}
+
+extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, int force_split, void* out, void* dbg, void* stream) {
     RAP_REQUIRE(heads == HEADS, "rap_test_fmha: heads must be 8");
     std::vector<int> cu(cu_host, cu_host + n_segments + 1);
-    std::vector<int4> tiles;
-    build_tiles(cu, tiles);
-    int4* dt = nullptr;
-    RAP_CUDA(cudaMalloc(&dt, 16 * tiles.size()));
-    RAP_CUDA(cudaMemcpy(dt, tiles.data(), 16 * tiles.size(), cudaMemcpyHostToDevice));
+    const FmhaSchedule sch = build_fmha_schedule(cu, heads, force_split != 0);
+    FmhaItem* dt = nullptr;
+    float* ws = nullptr;
+    int* counters = nullptr;
+    RAP_CUDA(cudaMalloc(&dt, sizeof(FmhaItem) * sch.items.size()));
+    RAP_CUDA(cudaMemcpy(dt, sch.items.data(), sizeof(FmhaItem) * sch.items.size(), cudaMemcpyHostToDevice));
+    RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
+    RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
+    RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
     CUtensorMap tm;
     int rc = make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128);
     if (!rc) {
         FmhaArgs f{};
-        f.tiles = dt; f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
-        rc = launch_fmha(tm, f, (int)tiles.size(), heads, static_cast<cudaStream_t>(stream));
+        f.items = dt; f.ws = ws; f.counters = counters; f.ws_pieces = sch.max_pieces;
+        f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
+        rc = launch_fmha(tm, f, (int)sch.items.size(), static_cast<cudaStream_t>(stream));
+        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, (int)sch.items.size(), static_cast<cudaStream_t>(stream));   // counters must have reset themselves
     }
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-    cudaFree(dt);
+    cudaFree(dt); cudaFree(ws); cudaFree(counters);
     return rc;
 }
 

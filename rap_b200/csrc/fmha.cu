@@ -11,6 +11,8 @@
 #include <cstdlib>
 
 #include "fmha.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include "sm100.cuh"
 
 namespace rap {
@@ -35,7 +37,7 @@ template <int NT> struct FCfg {
 constexpr uint32_t TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
 // Handing S back before the exponentials (possible whenever the gamma bound excludes overflow) was MEASURED slower: both query
 // tiles then run in lockstep and fight for the MUFU pipe, while the release-after-exp order staggers them naturally.
-constexpr bool kEarlyRelease = false;
+constexpr int kWsRow = 68;                       // floats per partial row: 64 outputs, reference exponent, row sum, 2 pad (16-byte rows)
 constexpr float kRowSumLimit = 32768.0f;         // a block row sum >= 2^15 means some P may leave the fp16 range: re-reference that row
 
 // One CTA = one 256-row query block (two 128-row tiles t=0,1) of one head; one CTA per SM.
@@ -52,11 +54,12 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const uint32_t sbase = smem_u32(smem);
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = blockIdx.y;
-    const int4 w = p.tiles[blockIdx.x];            // {q_row0, seg_start, seg_end, -}  (plan data, not produced by the previous kernel)
-    const int q0 = w.x, kv_begin = w.y, kv_end = w.z;
+    const FmhaItem item = p.items[blockIdx.x];     // plan data, not produced by the previous kernel
+    const int head = item.head;
+    const int q0 = item.q_row0, seg_end = item.seg_end;
+    const int kv_begin = item.kv_lo, kv_end = item.kv_hi;            // this piece's keys (the whole segment unless the unit was split)
     const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
-    const bool two = NT == 2 && q0 + BQ < kv_end;  // second 128-row tile has rows inside the segment
+    const bool two = NT == 2 && q0 + BQ < seg_end; // second 128-row tile has rows inside the segment
 
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t q_full = bar;
@@ -112,7 +115,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     } else if (warp == 1) {
         // Whole warp converged; only the UMMA / commit instructions are predicated on the elected lane.
         const bool leader = elect_one();
-        const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && leader;
+        const bool dbg_on = p.dbg && blockIdx.x == 0 && leader;
         constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV, false, false);   // A=Q K-major, B=K K-major, N=128
         constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A=P K-major, B=V MN-major, N=64
         const int nt = two ? 2 : 1;
@@ -168,7 +171,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             const uint32_t t_lane = tmem + (uint32_t(qd * 32) << 16);
             const uint32_t tm_s = t_lane + t * TM_TILE + TM_S, tm_p = t_lane + t * TM_TILE + TM_P, tm_o = t_lane + t * TM_TILE + TM_O;
             const float sl2 = p.scale_log2;
-            const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
             const float bound = p.score_bound ? p.score_bound[head] : INFINITY;
             float m_run = -INFINITY, l_run = 0.f;      // m_run: reference exponent (log2 domain), only raised lazily
             uint32_t sreg[4][32];
@@ -177,18 +180,20 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 mbar_wait(s_full(t), j & 1, 0x61);
                 tc_fence_after();
                 FMHA_TS(1);
+                // (Loading the scores in two halves, the second still in flight under the first 64 exponentials, was measured 7 % SLOWER:
+                // the extra tcgen05.wait::ld splits the exp stream and the two tiles lose their stagger.)
+                const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + c * 32, sreg[c]);
                 tmem_ld_wait();
                 // If no score of this head can exceed the current reference by 2^15 (bound from the qk-norm gammas), the stale-reference
                 // pass below cannot overflow, the slow path cannot trigger, and S_t can be handed back to the tensor core right now.
-                const bool early = kEarlyRelease && j > 0 && __all_sync(0xffffffffu, bound - m_run < 14.0f);
+                const bool early = p.early_release && j > 0 && __all_sync(0xffffffffu, bound - m_run < 14.0f);
                 if (early) {
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(s_free(t));
                 }
                 FMHA_TS(2);
-                const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
                 if (valid < BKV) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -214,7 +219,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 const f32x2 sl2x2 = pack2(sl2, sl2), nmx2 = pack2(-m_run, -m_run);
                 uint32_t preg[64];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 4; ++c) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         float ua, ub;
@@ -223,6 +228,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                         ls[(i >> 1) & 3] = fadd2(ls[(i >> 1) & 3], pack2(a, b));
                         preg[c * 16 + i / 2] = pack_half2(a, b);
                     }
+                }
                 float lsum;
                 {
                     float s0, s1;
@@ -299,16 +305,70 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 if (lane == 0) mbar_arrive(p_full(t));
                 FMHA_TS(7);
             }
-            // epilogue: O / l -> fp16
+            // epilogue
             mbar_wait(pv_done(t), (n_kv - 1) & 1, 0x63);
             tc_fence_after();
-            const float inv_l = 1.0f / l_run;
             const int row = q0 + t * BQ + r;
             uint32_t o[32], o2[32];
             tmem_ld32(tm_o, o);
             tmem_ld32(tm_o + 32, o2);
             tmem_ld_wait();
-            if (row < kv_end) {
+            bool write_out = true;
+            if (item.slot >= 0) {
+                // Split unit: publish this piece's un-normalised row (O, reference exponent, row sum); the piece that arrives last
+                // re-references all of them to the largest exponent, adds them up and writes the output.
+                const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
+                const int nthreads = two ? 256 : 128;
+                float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
+                float4* mine = reinterpret_cast<float4*>(unit_ws + ((size_t)piece * (NT * BQ) + t * BQ + r) * kWsRow);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mine[i / 4] = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+                    mine[8 + i / 4] = make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3]));
+                }
+                mine[16] = make_float4(m_run, l_run, 0.f, 0.f);
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                if (warp == 2 && lane == 0) {
+                    const int arrived = atomicAdd(p.counters + item.slot, 1);
+                    if (arrived == n_pieces - 1) p.counters[item.slot] = 0;      // every piece has arrived: ready for the next launch
+                    *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) = arrived == n_pieces - 1;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                write_out = *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) != 0;
+                if (write_out) {
+                    // Pieces are added in piece order from the workspace (this CTA's own rows included), so the result does not depend
+                    // on which piece happened to arrive last.
+                    __threadfence();
+                    const float* rows = unit_ws + (size_t)(t * BQ + r) * kWsRow;
+                    const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
+                    float m_all = -INFINITY;
+                    for (int q = 0; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
+                    l_run = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { o[i] = 0u; o2[i] = 0u; }
+                    for (int q = 0; q < n_pieces; ++q) {
+                        const float4* src = reinterpret_cast<const float4*>(rows + q * piece_stride);
+                        const float4 ml = __ldcg(src + 16);
+                        const float wq = ex2f(ml.x - m_all);
+                        l_run = fmaf(ml.y, wq, l_run);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 a = __ldcg(src + i / 4), b = __ldcg(src + 8 + i / 4);
+                            o[i] = __float_as_uint(fmaf(a.x, wq, __uint_as_float(o[i])));
+                            o[i + 1] = __float_as_uint(fmaf(a.y, wq, __uint_as_float(o[i + 1])));
+                            o[i + 2] = __float_as_uint(fmaf(a.z, wq, __uint_as_float(o[i + 2])));
+                            o[i + 3] = __float_as_uint(fmaf(a.w, wq, __uint_as_float(o[i + 3])));
+                            o2[i] = __float_as_uint(fmaf(b.x, wq, __uint_as_float(o2[i])));
+                            o2[i + 1] = __float_as_uint(fmaf(b.y, wq, __uint_as_float(o2[i + 1])));
+                            o2[i + 2] = __float_as_uint(fmaf(b.z, wq, __uint_as_float(o2[i + 2])));
+                            o2[i + 3] = __float_as_uint(fmaf(b.w, wq, __uint_as_float(o2[i + 3])));
+                        }
+                    }
+                }
+            }
+            const float inv_l = 1.0f / l_run;
+            if (write_out && row < seg_end) {
                 uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
@@ -332,7 +392,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
 }  // namespace
 
 template <int NT>
-static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int heads, cudaStream_t st) {
+static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_items, cudaStream_t st) {
     using F = FCfg<NT>;
     static bool configured = false;
     if (!configured) {
@@ -340,7 +400,7 @@ static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, i
         configured = true;
     }
     ProfScope _ps(KC_FMHA, st);
-    RAP_CUDA(launch_pdl(fmha_kernel<NT>, dim3(n_tiles, heads), dim3(F::kThreads), F::SMEM_BYTES, st, tm_qkv, a));
+    RAP_CUDA(launch_pdl(fmha_kernel<NT>, dim3(n_items), dim3(F::kThreads), F::SMEM_BYTES, st, tm_qkv, a));
     note_launch();
     return RAP_OK;
 }
@@ -351,9 +411,84 @@ int fmha_rows_per_cta() {
     return rows;
 }
 
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_tiles, int heads, cudaStream_t st) {
-    RAP_REQUIRE(n_tiles > 0 && heads > 0 && a.d_model == heads * HD, "fmha: bad args (tiles=%d heads=%d d=%d)", n_tiles, heads, a.d_model);
-    return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, a, n_tiles, heads, st) : launch_t<2>(tm_qkv, a, n_tiles, heads, st);
+size_t FmhaSchedule::workspace_floats() const { return (size_t)n_slots * max_pieces * fmha_rows_per_cta() * kWsRow; }
+
+// Every (query block, head) unit costs its number of 128-key blocks.  Units are issued longest first; the hardware hands the next
+// CTA to whichever SM frees up, so whole waves balance by themselves and only the last, partially filled wave leaves SMs idle
+// (cfg2: 256 units on 148 SMs = 13.5 % of the kernel).  The R units of that wave are therefore cut along the key axis:
+//   * R <= SMs/2: each into k = SMs/R equal pieces;
+//   * otherwise: each into a big piece (its own SM) and a small one, q = ceil(R / idle SMs) small pieces per idle SM, sized 1/(q+1).
+FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool force_split) {
+    static int split = -1;
+    if (split < 0) { const char* e = getenv("RAP_FMHA_SPLIT"); split = (e && atoi(e) == 0) ? 0 : 1; }
+    const int rows = fmha_rows_per_cta();
+    const int slots_per_wave = num_sms() * (rows == 128 ? 2 : 1);
+    constexpr int kMaxPieces = 8;
+    struct Unit { int q, s0, s1, head, blocks; };
+    std::vector<Unit> units;
+    for (int h = 0; h < heads; ++h)
+        for (size_t s = 0; s + 1 < cu.size(); ++s)
+            for (int q = cu[s]; q < cu[s + 1]; q += rows) units.push_back({q, cu[s], cu[s + 1], h, (cu[s + 1] - cu[s] + BKV - 1) / BKV});
+    std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.blocks > b.blocks; });
+    FmhaSchedule sch;
+    const int U = (int)units.size();
+    // A piece costs about kPieceOverhead key blocks on top of its own (CTA start-up, pipeline fill, partial-row round trip through L2;
+    // measured with tools/fmha_split_sweep.py: ~7 us against 1.55 us per block).  Splitting is skipped when it would not pay.
+    constexpr double kPieceOverhead = 4.5;
+    int R = (split || force_split) ? U % slots_per_wave : 0;
+    int k_equal = 0, q_small = 0;
+    static double frac_env = -1.0;                        // RAP_FMHA_SMALL_FRAC: override of the small piece's share (tuning aid)
+    if (frac_env < 0.0) { const char* e = getenv("RAP_FMHA_SMALL_FRAC"); frac_env = e ? atof(e) : 0.0; }
+    double small_frac = 0.0;
+    if (R > 0) {
+        const double o_rel = kPieceOverhead / std::max(1, units[U - 1].blocks);
+        if (2 * R <= slots_per_wave) {
+            k_equal = std::min(slots_per_wave / R, kMaxPieces);
+            if (!force_split && 1.0 / k_equal + o_rel > 0.92) R = 0;
+        } else {
+            q_small = (R + (slots_per_wave - R) - 1) / (slots_per_wave - R);
+            small_frac = frac_env > 0.0 ? frac_env : (1.0 - 2.0 * o_rel) / (q_small + 1);      // q (x + o) = 1 - x + o
+            if (force_split) small_frac = std::max(small_frac, 1.0 / (q_small + 1));
+            else if (frac_env <= 0.0 && small_frac - o_rel < 0.08) R = 0;                           // the last wave would shrink by < 8 %
+        }
+    }
+    auto whole = [&](const Unit& u) { sch.items.push_back({u.q, u.s0, u.s1, u.head, u.s0, u.s1, -1, 1 << 8}); };
+    for (int i = 0; i < U - R; ++i) whole(units[i]);
+    std::vector<FmhaItem> later;
+    for (int i = U - R; i < U; ++i) {
+        const Unit& u = units[i];
+        std::vector<int> cuts;                            // block counts of the pieces, first = biggest
+        if (k_equal >= 2) {
+            const int k = std::min(k_equal, u.blocks);
+            for (int p = 0; p < k; ++p) cuts.push_back(u.blocks / k + (p < u.blocks % k ? 1 : 0));
+        } else if (q_small > 0) {
+            const int small = std::max(1, (int)(u.blocks * small_frac + 0.5));
+            if (u.blocks - small >= 1) { cuts.push_back(u.blocks - small); cuts.push_back(small); }
+        }
+        if (cuts.size() < 2) { whole(u); continue; }
+        const int slot = sch.n_slots++;
+        sch.max_pieces = std::max(sch.max_pieces, (int)cuts.size());
+        int lo = u.s0;
+        for (size_t p = 0; p < cuts.size(); ++p) {
+            const int hi = std::min(u.s1, lo + cuts[p] * BKV);
+            FmhaItem it{u.q, u.s0, u.s1, u.head, lo, hi, slot, (int)p | ((int)cuts.size() << 8)};
+            if (p == 0) sch.items.push_back(it); else later.push_back(it);
+            lo = hi;
+        }
+    }
+    // big pieces were appended in unit order; the smaller pieces follow, piece index by piece index
+    std::stable_sort(later.begin(), later.end(), [](const FmhaItem& a, const FmhaItem& b) { return (a.piece & 0xff) < (b.piece & 0xff); });
+    sch.items.insert(sch.items.end(), later.begin(), later.end());
+    return sch;
+}
+
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_items, cudaStream_t st) {
+    RAP_REQUIRE(n_items > 0 && a.items && a.d_model % HD == 0, "fmha: bad args (items=%d d=%d)", n_items, a.d_model);
+    static int early = -1;
+    if (early < 0) { const char* e = getenv("RAP_FMHA_EARLY"); early = (e && atoi(e) == 1) ? 1 : 0; }
+    FmhaArgs b = a;
+    b.early_release = early && a.score_bound;
+    return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, b, n_items, st) : launch_t<2>(tm_qkv, b, n_items, st);
 }
 
 }  // namespace rap

@@ -1,21 +1,48 @@
 // Varlen FMHA launcher (see fmha.cu).
 #pragma once
+#include <vector>
+
 #include "common.h"
 
 namespace rap {
 
+// One CTA's work: a query block (rows_per_cta rows) of one head against the keys [kv_lo, kv_hi) of its segment.  Blocks whose key range
+// was split to fill the last wave (slot >= 0) leave un-normalised partial rows in the workspace; the last piece to finish combines them.
+struct FmhaItem {
+    int q_row0, seg_start, seg_end, head;
+    int kv_lo, kv_hi;      // key rows of this piece, kv_lo a multiple of 128 rows from seg_start, kv_hi = seg_end or block aligned
+    int slot;              // partial-result slot of the (query block, head) unit, or -1: whole key range, write the output directly
+    int piece;             // piece index | (number of pieces << 8)
+};
+
+struct FmhaSchedule {
+    std::vector<FmhaItem> items;   // launch order: whole units first (longest first), then the big pieces, then the small ones
+    int n_slots = 0;               // units that were split
+    int max_pieces = 0;            // workspace stride: pieces per slot
+    size_t workspace_floats() const;
+};
+
+// Work list for one attention launch over segments cu[0..n] (query blocks never straddle a segment).  With split enabled (default;
+// RAP_FMHA_SPLIT=0 disables) the units of the last, partially filled wave are cut along the key axis so that every SM ends together.
+// force_split (tests): cut the last wave even where the cost model says it does not pay.
+FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool force_split = false);
+
 struct FmhaArgs {
-    const int4* tiles;   // device: {q_row0, seg_start, seg_end, 0} per 256-row query block (two 128-row tiles)
+    const FmhaItem* items;   // device copy of FmhaSchedule::items
     __half* out;         // [T, d_model] fp16, head h at columns [64h, 64h+64)
     int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
     float scale_log2;    // log2(e) / sqrt(head_dim)
     const float* score_bound;  // [heads] upper bound of |score * scale_log2| (from the qk-norm gammas), or null = unknown
-    long long* dbg;      // optional clock64() timeline of CTA (0,0): [iter][16] slots (tools/fmha_timeline.py), else null
+    int early_release;   // hand S back before the exponentials when score_bound rules out the slow path (set by launch_fmha from RAP_FMHA_EARLY)
+    float* ws;           // partial rows [slot][piece][rows_per_cta][68] (64 un-normalised outputs, reference exponent, row sum, pad), or null
+    int* counters;       // [n_slots] arrival counters, zero between launches (the combining CTA resets its counter)
+    int ws_pieces;       // FmhaSchedule::max_pieces
+    long long* dbg;      // optional clock64() timeline of CTA 0: [iter][16] slots (tools/fmha_timeline.py), else null
 };
 
 // tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.
-// Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM) -- tile lists must match.
+// Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM) -- schedules must match.
 int fmha_rows_per_cta();
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_tiles, int heads, cudaStream_t st);
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_items, cudaStream_t st);
 
 }  // namespace rap

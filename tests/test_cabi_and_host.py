@@ -138,3 +138,45 @@ def test_split_parts_and_repeat_helpers():
         split_parts(x, torch.tensor([[10]]))
     r = repeat_by_cu_seqlens(torch.tensor([[1.], [2.]]), torch.tensor([0, 2, 5]))
     assert r.flatten().tolist() == [1, 1, 2, 2, 2]
+
+
+def _fmha_schedule(cu, heads=8, force=1):
+    import ctypes as C
+    from rap_b200 import _lib
+    cu_a = _lib.i32_array(cu)
+    n = _lib.lib.rap_fmha_schedule(cu_a, len(cu) - 1, heads, force, None, 0, None, None)
+    buf, ns, mp = (C.c_int32 * (8 * n))(), C.c_int(), C.c_int()
+    assert _lib.lib.rap_fmha_schedule(cu_a, len(cu) - 1, heads, force, buf, n, C.byref(ns), C.byref(mp)) == n
+    return np.array(buf).reshape(n, 8), ns.value, mp.value
+
+
+@pytest.mark.parametrize("cu", [[0, 4096, 8192], [0, 8192], [0, 512, 1024], [0, 16384], [0, 3000, 5000, 9000], [0, 100], [0, 130, 700, 701]])
+def test_fmha_schedule_covers_every_key_block_once(cu):
+    """Host logic of the attention launch: whole units plus key-split pieces must tile (query block, head) x keys exactly, pieces of a
+    unit share a slot and are numbered 0..n-1, and big pieces are issued before small ones."""
+    items, n_slots, max_pieces = _fmha_schedule(cu)
+    seen = {}
+    for q0, s0, s1, head, lo, hi, slot, piece in items.tolist():
+        assert s0 <= q0 < s1 and s0 <= lo < hi <= s1 and (lo - s0) % 128 == 0 and (hi == s1 or (hi - s0) % 128 == 0)
+        n_p, idx = piece >> 8, piece & 0xff
+        assert (slot < 0) == (n_p == 1) and idx < n_p <= max(max_pieces, 1)
+        seen.setdefault((q0, head), []).append((lo, hi, slot, idx, n_p))
+    q_blocks = sum(-(-(b - a) // 256) for a, b in zip(cu[:-1], cu[1:]))
+    assert len(seen) == 8 * q_blocks
+    slots = set()
+    for (q0, head), pieces in seen.items():
+        pieces.sort()
+        seg = next((a, b) for a, b in zip(cu[:-1], cu[1:]) if a <= q0 < b)
+        assert pieces[0][0] == seg[0] and pieces[-1][1] == seg[1] and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        assert len({p[2] for p in pieces}) == 1 and sorted(p[3] for p in pieces) == list(range(pieces[0][4]))
+        if pieces[0][2] >= 0:
+            slots.add(pieces[0][2])
+    assert slots == set(range(n_slots))
+    # cfg2 (the headline layout): 148 whole units, then 108 big and 108 small pieces -> every SM ends together
+    if cu in ([0, 4096, 8192], [0, 8192]):
+        assert (items[:148, 6] < 0).all() and n_slots == 108 and max_pieces == 2
+        blocks = (items[:, 5] - items[:, 4]) // 128
+        assert (blocks[148:256] == blocks[148]).all() and (blocks[256:] == blocks[256]).all() and blocks[148] == 3 * blocks[256]
+        # the cost model (piece overhead ~4.5 key blocks) keeps the 32-block per-view launch whole and cuts the 64-block per-scene one
+        plain, n_plain, _ = _fmha_schedule(cu, force=0)
+        assert (n_plain == 0 and len(plain) == 256) if cu == [0, 4096, 8192] else (n_plain == 108 and len(plain) == 364)

@@ -86,8 +86,11 @@ def test_gemm_geglu(rap):
     assert (out16.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048]])
-def test_fmha_varlen(rap, lens):
+# force=1: the units of the last, partially filled wave are split along the keys and recombined even where the cost model would not
+@pytest.mark.parametrize("force", [0, 1])
+@pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048], [512, 512], [2000, 1500],
+                                  [4096, 4096], [8192], [16384]])
+def test_fmha_varlen(rap, lens, force):
     g = torch.Generator("cuda").manual_seed(sum(lens))
     T = sum(lens)
     qkv = torch.randn(T, 3, 8, 64, device="cuda", generator=g)
@@ -95,7 +98,7 @@ def test_fmha_varlen(rap, lens):
     qkv = qkv.half().contiguous()
     out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array(cu), len(lens), out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array(cu), len(lens), force, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
     _sync_check(rap)
     ref = torch.empty(T, 8, 64, device="cuda")
     for s, e in zip(cu[:-1], cu[1:]):
@@ -116,7 +119,7 @@ def test_fmha_lazy_reference_overflow_path(rap):
     qkv[128:384, 1] *= 0.3                                       # intermediate growth
     qkv = qkv.half().contiguous()
     out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
-    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array([0, T]), 1, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array([0, T]), 1, 1, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
     _sync_check(rap)
     q, k, v = (qkv[:, i].float().transpose(0, 1) for i in range(3))
     ref = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1)
