@@ -370,6 +370,7 @@ struct rap_plan {
     const float* cond = nullptr;
     const uint8_t* anchor = nullptr;
     bool condition_set = false;
+    size_t resid_bytes = 0;        // bytes of [h | x16]: the fp32 residual stream and its LayerNorm'd fp16 copy
 };
 
 namespace {
@@ -427,8 +428,10 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T); pl->zero_rows = s.take<int>(T);
     pl->items_part = s.take<FmhaItem>(tp.size()); pl->items_batch = s.take<FmhaItem>(tb.size());
     pl->fmha_ws = s.take<float>(fmha_ws_floats); pl->fmha_counters = s.take<int>(fmha_slots + 1);
-    pl->h = s.take<float>(Tp * D); pl->h_static = s.take<float>(Tp * D); pl->x_t = s.take<float>(Tp * 3); pl->tbuf = s.take<float>(pl->n_cap);
-    pl->x16 = s.take<__half>(Tp * D); pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
+    pl->h = s.take<float>(Tp * D); pl->x16 = s.take<__half>(Tp * D);       // adjacent: one L2 persistence window covers the residual stream
+    pl->resid_bytes = (size_t)(reinterpret_cast<char*>(pl->x16 + Tp * D) - reinterpret_cast<char*>(pl->h));
+    pl->h_static = s.take<float>(Tp * D); pl->x_t = s.take<float>(Tp * 3); pl->tbuf = s.take<float>(pl->n_cap);
+    pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
     pl->a_s = s.take<__half>(Tp * 128); pl->a_x = s.take<__half>(Tp * 64);
     pl->hh16 = s.take<__half>(Tp * D); pl->y1 = s.take<__half>(Tp * D); pl->y2 = s.take<__half>(Tp * (D / 2));
     pl->ada_e0 = s.take<float>((size_t)pl->n_cap * ADA_CH); pl->ada_e1 = s.take<float>((size_t)pl->n_cap * M * D);
@@ -478,6 +481,35 @@ extern "C" int rap_plan_set_condition(rap_plan_t* pl, const float* cond, const f
 namespace {
 
 // AdaLN scale/shift for n timesteps already in pl->tbuf: table[n][module][scale 512 | shift 512]
+// The residual stream h (fp32, re-read and re-written by three GEMM epilogues and three LayerNorms per layer) and its fp16 LN copy are
+// kept in L2 by an access-policy window on the launching stream: the per-layer working set (qkv, attention output, GEGLU mid) is larger
+// than L2, so without it every epilogue write of h turns into an HBM write-back and every re-read into an HBM read.
+// RAP_L2_PERSIST=0 disables (A/B measurements).  Failures are ignored: it is a hint.
+void pin_residual_stream(rap_plan* pl, cudaStream_t st) {
+    static int enabled = -1;
+    static size_t carve = 0, max_window = 0;
+    if (enabled < 0) {
+        const char* e = getenv("RAP_L2_PERSIST");
+        enabled = (e && atoi(e) == 0) ? 0 : 1;
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess) carve = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) max_window = (size_t)v;
+        if (!carve || !max_window || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(carve, (size_t)48 << 20)) != cudaSuccess) enabled = 0;
+        carve = std::min(carve, (size_t)48 << 20);
+        cudaGetLastError();
+    }
+    if (!enabled || !pl->resid_bytes) return;
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = pl->h;
+    attr.accessPolicyWindow.num_bytes = std::min(pl->resid_bytes, max_window);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+
 int ada_table(rap_plan* pl, int n, cudaStream_t st) {
     rap_dit* d = pl->dit;
     RAP_TRY(launch_timestep_sincos(pl->tbuf, pl->ada_e0, n, st));
@@ -541,6 +573,7 @@ extern "C" int rap_dit_forward(rap_plan_t* pl, const float* x, const float* time
     RAP_REQUIRE(pl->condition_set, "rap_dit_forward: call rap_plan_set_condition first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RAP_CUDA(cudaMemcpyAsync(pl->tbuf, timesteps, sizeof(float) * pl->B, cudaMemcpyDeviceToDevice, st));
+    pin_residual_stream(pl, st);
     RAP_TRY(ada_table(pl, pl->B, st));
     RAP_TRY(dit_body(pl, x, 0, true, st));
     RAP_TRY(launch_head_final(pl->y2, pl->dit->wh4, pl->T, velocity, nullptr, 0.f, 0.f, nullptr, nullptr, st));
@@ -555,6 +588,7 @@ extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps,
     RAP_REQUIRE(num_steps >= 1 && num_steps <= pl->n_cap, "rap_sample_euler: num_steps=%d outside [1,%d] (max_timesteps of the plan)", num_steps, pl->n_cap);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t row = (size_t)pl->T * 3;
+    pin_residual_stream(pl, st);
     sampler_timesteps_kernel<<<1, 64, 0, st>>>(pl->tbuf, num_steps);
     RAP_CUDA(cudaGetLastError());
     note_launch(1);

@@ -18,12 +18,13 @@ def run(name, epi, bn, M, N, K):
     ev[1].record(); torch.cuda.synchronize()
     d = dbg.cpu().numpy(); t0 = d[0][0]
     print(f"== {name}: M={M} N={N} K={K} BN={bn}: {ev[0].elapsed_time(ev[1])*1e3:.1f} us, {2*M*N*K/ev[0].elapsed_time(ev[1])/1e9:.0f} TFLOP/s")
-    for t in range(4):
+    for t in range(2 if epi == 0 else 4):
         r = d[t]
         if r[0] == 0: break
+        if t == 0 and epi == 0:
+            c = d[2:4].reshape(-1)
+            print("  epilogue chunks (warp 2): " + " | ".join(f"c{k}: ld {c[4*k+1]-c[4*k]} stage {c[4*k+2]-c[4*k+1]} add+store {c[4*k+3]-c[4*k+2]} (start {c[4*k]-r[6]})" for k in range(4) if c[4*k]))
         print(f"  tile{t}: prod [{r[0]-t0},{r[1]-t0}]  mma wait_acc {r[3]-r[2]} issue_span {r[4]-r[3]} (start {r[2]-t0})  epi start {r[5]-t0} acc_ready {r[6]-t0} done {r[7]-t0} (epi work {r[7]-r[6]})")
-run("qkv", 2, 256, 8192, 1536, 512)
-run("geglu", 3, 256, 8192, 4096, 512)
 run("outproj f32", 0, 256, 8192, 512, 512)
 run("ff2 f32", 0, 256, 8192, 512, 2048)
 run("outproj f32 bn128", 0, 128, 8192, 512, 512)
