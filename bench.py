@@ -270,6 +270,30 @@ def run_cuda(args) -> None:
                                  "pairs_per_s_including_features": 1.0 / (t_dev / (K * B) + t_fx)}
         except Exception as e:  # pragma: no cover
             line["extractor"] = {"error": str(e)[:200]}
+        # keypoint selection in front of the extractor, steady state, device-resident inputs
+        try:
+            import numpy as np
+            from rap_b200.dataset_process.utils import dataset_utils as du
+            from rap_b200.dataset_process.utils.point_sampling_utils import sample_farthest_points
+            g = torch.Generator(device=dev).manual_seed(3)
+            raw = torch.randn(1_000_000, 3, device=dev, generator=g) * torch.tensor([40.0, 40.0, 6.0], device=dev)
+            cloud = torch.randn(2, 100_000, 3, device=dev, generator=g) * torch.tensor([30.0, 30.0, 4.0], device=dev)
+            lens, ks = torch.tensor([100_000, 100_000]), torch.tensor([5000, 5000])
+
+            def timed(fn, n):
+                fn(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record(); torch.cuda.synchronize()
+                return a.elapsed_time(b) / n
+            line["keypoint_selection"] = {
+                "voxel_downsample_ms": timed(lambda: du.voxel_down_sample_torch(raw, 0.5), 5), "voxel_workload": "1e6 points, 0.5 m voxels",
+                "fps_ms": timed(lambda: sample_farthest_points(cloud, lengths=lens, K=ks, random_start_point=False), 3),
+                "fps_workload": "2 clouds x 100000 points -> 5000 keypoints each (one 8-CTA cluster per cloud)"}
+        except Exception as e:  # pragma: no cover
+            line["keypoint_selection"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_sample(steps=1, warmup=0, budget_s=30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

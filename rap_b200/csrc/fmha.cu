@@ -54,6 +54,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const uint32_t sbase = smem_u32(smem);
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[15] = clock64();                 // CTA entry
     const FmhaItem item = p.items[blockIdx.x];     // plan data, not produced by the previous kernel
     const int head = item.head;
     const int q0 = item.q_row0, seg_end = item.seg_end;
@@ -384,6 +385,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             }
         }
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[16 + 15] = clock64();            // softmax warp 2 done (epilogue written)
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);

@@ -22,3 +22,8 @@ for j in range(8, 12):
     row = d[j]
     print(j, "t0:", row[8] - row[7], row[9] - row[8], row[10] - row[9], " t1:", row[12] - row[10], row[13] - row[12], row[14] - row[13], " loop period", d[j + 1][8] - row[8])
 per = np.diff(d[4:60, 0]); print("mean softmax period", per.mean(), "cycles; ideal MUFU-bound 1024/tile")
+
+t_in, t_out = d[0][15], d[1][15]
+starts = d[:nkv, 0]
+print(f"CTA 0: entry -> first S wait {starts[0]-t_in} cycles; first 6 block periods {np.diff(starts[:7]).tolist()}; last 6 {np.diff(starts[-7:]).tolist()}")
+print(f"       last block start -> softmax done {t_out-starts[-1]} cycles; whole CTA {t_out-t_in} cycles = {nkv} blocks x {(t_out-t_in)/nkv:.0f}")
