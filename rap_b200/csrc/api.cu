@@ -157,7 +157,6 @@ struct rap_dit {
     // per layer
     std::vector<__half*> wqkv[2], wout[2], w1, w2;
     std::vector<float*> bout[2], gamma[2] /* [2(q,k),8,64] */, b1, b2, ffn_w, ffn_b;
-    float *ln_u_ff = nullptr, *ln_v_ff = nullptr;   // [L][2*FF_INNER]: LN-folding tables of the (static, affine) ff_norm in front of the GEGLU GEMM
     float* score_bound = nullptr;   // [2L][8]: per (layer, block, head) bound of |q.k| * log2(e)/8 implied by the qk-norm gammas
     // AdaLN MLPs, module m = 2*layer + blk
     __half *ada_w1 = nullptr, *ada_w2 = nullptr, *ada_w3 = nullptr;
@@ -216,8 +215,7 @@ extern "C" int rap_dit_create(rap_dit_t** out, int embed_dim, int num_layers, in
     size_t halfs = (size_t)D * 64 + (size_t)D * 128 + (size_t)L * (2 * 3 * D * D + 2 * D * D + 2 * FF_INNER * D + D * FF_INNER) +
                    (size_t)M * (D * ADA_CH + D * D + 2 * D * D) + (size_t)D * D + (size_t)(D / 2) * D;
     size_t floats = (size_t)D + 2 * D + (size_t)L * (2 * D + 2 * 2 * HEADS * HD + 2 * FF_INNER + D + 2 * D) + (size_t)M * (D + D + 2 * D) + D + D / 2 + 3 * (D / 2);
-    floats += (size_t)L * 2 * 2 * FF_INNER;      // LN-folding tables of ff_norm
-    d->slab.size = halfs * 2 + floats * 4 + 256 * (64 + 24 * (size_t)L);
+    d->slab.size = halfs * 2 + floats * 4 + 256 * (64 + 20 * (size_t)L);
     if (cudaMalloc(&d->slab.base, d->slab.size) != cudaSuccess) { delete d; return fail(RAP_ENOMEM, "rap_dit_create: cudaMalloc(%zu) failed", d->slab.size); }
     cudaMemset(d->slab.base, 0, d->slab.size);
     Slab& s = d->slab;
@@ -276,7 +274,6 @@ extern "C" int rap_dit_create(rap_dit_t** out, int embed_dim, int num_layers, in
         add_entry(d, p + "ff.net.2.bias", d->b2[l], false, plain(1, D), D);
     }
     d->score_bound = s.take<float>((size_t)M * HEADS);
-    d->ln_u_ff = s.take<float>((size_t)L * 2 * FF_INNER); d->ln_v_ff = s.take<float>((size_t)L * 2 * FF_INNER);
     d->wh0 = s.take<__half>((size_t)D * D); d->bh0 = s.take<float>(D);
     d->wh2 = s.take<__half>((size_t)(D / 2) * D); d->bh2 = s.take<float>(D / 2);
     d->wh4 = s.take<float>(3 * (D / 2));
@@ -348,12 +345,8 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
             RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, f32_bn()));
         }
         RAP_TRY(make_tmap_f16_sw128(&d->tm_w1[l], d->w1[l], 2 * FF_INNER, D, D, 256));
-        // ff_norm (affine LayerNorm, layer.py:163) folded into the GEGLU GEMM: x * weight is the operand, u = W1 weight, v = W1 bias_ln + b1
-        RAP_TRY(launch_ln_fold(d->w1[l], d->b1[l], d->ffn_w[l], d->ffn_b[l], 0, 0.0f, 1, 2 * FF_INNER, d->ln_u_ff + (size_t)l * 2 * FF_INNER,
-                               d->ln_v_ff + (size_t)l * 2 * FF_INNER, 0, nullptr));
         RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, f32_bn()));
     }
-    RAP_CUDA(cudaDeviceSynchronize());
     d->finalized = true;
     return RAP_OK;
 }
@@ -373,8 +366,6 @@ struct rap_plan {
     float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
     __half *x16 = nullptr, *attn16 = nullptr, *qkv = nullptr, *ffmid = nullptr, *a_s = nullptr, *a_x = nullptr, *hh16 = nullptr, *y1 = nullptr, *y2 = nullptr;
     float *ada_e0 = nullptr, *ada_e1 = nullptr, *ada_e2 = nullptr, *ada_tab = nullptr;
-    float *ln_stats = nullptr;                     // [Tp][<=8 column slices][sum, sum of squares] of the current residual rows
-    float *ln_u_qkv = nullptr, *ln_v_qkv = nullptr; // [n_cap][M][3D] LN-folding tables of the AdaLN in front of every QKV GEMM
     CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn;
     const float* cond = nullptr;
     const uint8_t* anchor = nullptr;
@@ -429,7 +420,6 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     need(4 * Tp * D); need(4 * Tp * D); need(4 * Tp * 3); need(4 * (size_t)pl->n_cap);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * 3 * D); need(2 * Tp * FF_INNER); need(2 * Tp * 128); need(2 * Tp * 64);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * (D / 2));
-    need(4 * Tp * 16); need(4 * (size_t)pl->n_cap * M * 3 * D); need(4 * (size_t)pl->n_cap * M * 3 * D);
     need(4 * (size_t)pl->n_cap * ADA_CH); need(4 * (size_t)pl->n_cap * M * D); need(4 * (size_t)pl->n_cap * M * D); need(4 * (size_t)pl->n_cap * M * 2 * D);
     bytes += 4096;
     if (cudaMalloc(&pl->ws, bytes) != cudaSuccess) { delete pl; return fail(RAP_ENOMEM, "rap_plan_create: cudaMalloc(%zu) failed", bytes); }
@@ -444,7 +434,6 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     pl->attn16 = s.take<__half>(Tp * D); pl->qkv = s.take<__half>(Tp * 3 * D); pl->ffmid = s.take<__half>(Tp * FF_INNER);
     pl->a_s = s.take<__half>(Tp * 128); pl->a_x = s.take<__half>(Tp * 64);
     pl->hh16 = s.take<__half>(Tp * D); pl->y1 = s.take<__half>(Tp * D); pl->y2 = s.take<__half>(Tp * (D / 2));
-    pl->ln_stats = s.take<float>(Tp * 16); pl->ln_u_qkv = s.take<float>((size_t)pl->n_cap * M * 3 * D); pl->ln_v_qkv = s.take<float>((size_t)pl->n_cap * M * 3 * D);
     pl->ada_e0 = s.take<float>((size_t)pl->n_cap * ADA_CH); pl->ada_e1 = s.take<float>((size_t)pl->n_cap * M * D);
     pl->ada_e2 = s.take<float>((size_t)pl->n_cap * M * D); pl->ada_tab = s.take<float>((size_t)pl->n_cap * M * 2 * D);
     if (s.used > s.size) { cudaFree(pl->ws); delete pl; return fail(RAP_ESTATE, "rap_plan_create: workspace overflow"); }
@@ -527,11 +516,6 @@ int ada_table(rap_plan* pl, int n, cudaStream_t st) {
     RAP_TRY(launch_ada_linear(d->ada_w1, d->ada_b1, pl->ada_e0, 0, pl->ada_e1, n, d->M, D, ADA_CH, 1, st));
     RAP_TRY(launch_ada_linear(d->ada_w2, d->ada_b2, pl->ada_e1, 1, pl->ada_e2, n, d->M, D, D, 1, st));
     RAP_TRY(launch_ada_linear(d->ada_w3, d->ada_b3, pl->ada_e2, 1, pl->ada_tab, n, d->M, 2 * D, D, 0, st));
-    for (int m = 0; m < d->M; ++m) {                 // LN folding: u = Wqkv (1 + scale), v = Wqkv shift per timestep / scene row
-        const float* ss = pl->ada_tab + (size_t)m * 2 * D;
-        RAP_TRY(launch_ln_fold(d->wqkv[m & 1][m >> 1], nullptr, ss, ss + D, d->M * 2 * D, 1.0f, n, 3 * D, pl->ln_u_qkv + (size_t)m * 3 * D,
-                               pl->ln_v_qkv + (size_t)m * 3 * D, d->M * 3 * D, st));
-    }
     return RAP_OK;
 }
 
@@ -542,52 +526,35 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
     const int T = pl->T, M = d->M;
     const float scale_log2 = 1.4426950408889634f / 8.0f;   // log2(e) / sqrt(64)
     RAP_TRY(launch_posenc_x(x, pl->a_x, T, st));
-    const int row_stride = M * 2 * D;
-    const int* rows = per_scene ? pl->scene_of_tok : pl->zero_rows;
-    const int nslice = D / (f32_bn() / 2);           // column slices (= epilogue warps across a row) of the fp32 GEMMs
-    // Every GEMM that writes the residual stream also writes the fp16 operand of the next GEMM (x times the next LayerNorm's scale) and
-    // per-row partial moments; the next GEMM normalises in its epilogue (gemm.cuh, "LN folding") -- there is no LayerNorm kernel.
-    auto next_adaln = [&](GemmArgs& g, int m) {      // next consumer: QKV GEMM behind AdaLN module m
-        g.out16 = pl->x16; g.ld16 = D; g.ln_mul = pl->ada_tab + ((size_t)tab_row0 * M + m) * 2 * D; g.ln_row_of_tok = rows; g.ln_row_stride = row_stride;
-        g.ln_one_plus = 1.0f; g.ln_stats_out = pl->ln_stats; g.ln_nslice = nslice;
-    };
     {
         GemmArgs g{};
         g.M = T; g.N = D; g.K = 64; g.addend = pl->h_static; g.out32 = pl->h; g.ld32 = D;
-        next_adaln(g, 0);
         RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ax, d->tm_emb_x, g, st));
     }
+    const int row_stride = M * 2 * D;
     for (int l = 0; l < d->L; ++l) {
         for (int b = 0; b < 2; ++b) {
-            const int m = 2 * l + b;
+            const float* ss = pl->ada_tab + ((size_t)tab_row0 * M + (2 * l + b)) * 2 * D;
+            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, ss, ss + D, row_stride, per_scene ? pl->scene_of_tok : pl->zero_rows, 1.0f, st));
             GemmArgs q{};
             q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
-            q.ln_stats = pl->ln_stats; q.ln_nslice = nslice; q.ln_row_of_tok = rows; q.ln_uv_stride = M * 3 * D;
-            q.ln_u = pl->ln_u_qkv + ((size_t)tab_row0 * M + m) * 3 * D; q.ln_v = pl->ln_v_qkv + ((size_t)tab_row0 * M + m) * 3 * D;
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
             FmhaArgs f{};
             f.items = b == 0 ? pl->items_part : pl->items_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;
             f.ws_pieces = b == 0 ? pl->fmha_pieces_part : pl->fmha_pieces_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
-            f.score_bound = d->score_bound + (size_t)m * HEADS;
+            f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
-            if (b == 0) next_adaln(o, m + 1);
-            else {                                       // next consumer: GEGLU GEMM behind the affine ff_norm
-                o.out16 = pl->x16; o.ld16 = D; o.ln_mul = d->ffn_w[l]; o.ln_row_of_tok = pl->zero_rows; o.ln_row_stride = 0; o.ln_one_plus = 0.0f;
-                o.ln_stats_out = pl->ln_stats; o.ln_nslice = nslice;
-            }
             RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_attn16, d->tm_out[b][l], o, st));
         }
+        RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, pl->zero_rows, 0.0f, st));
         GemmArgs f1{};
         f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER;
-        f1.ln_stats = pl->ln_stats; f1.ln_nslice = nslice; f1.ln_row_of_tok = pl->zero_rows; f1.ln_uv_stride = 0;
-        f1.ln_u = d->ln_u_ff + (size_t)l * 2 * FF_INNER; f1.ln_v = d->ln_v_ff + (size_t)l * 2 * FF_INNER;
         RAP_TRY(launch_gemm(EPI_GEGLU, 256, pl->tm_x16, d->tm_w1[l], f1, st));
         GemmArgs f2{};
         f2.M = T; f2.N = D; f2.K = FF_INNER; f2.bias = d->b2[l]; f2.addend = pl->h; f2.out32 = pl->h; f2.ld32 = D;
-        if (l == d->L - 1) { f2.out16 = pl->hh16; f2.ld16 = D; }      // head input: plain fp16 copy
-        else next_adaln(f2, 2 * (l + 1));
+        if (l == d->L - 1) { f2.out16 = pl->hh16; f2.ld16 = D; }
         RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ffmid, d->tm_w2[l], f2, st));
     }
     GemmArgs h0{};

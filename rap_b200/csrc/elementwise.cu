@@ -138,32 +138,6 @@ ada_linear_kernel(const __half* __restrict__ W, const float* __restrict__ b, con
     }
 }
 
-// LN folding tables (gemm.cuh): for every table row i (timestep or scene) and output column o of a GEMM that consumes LN(x)(one_plus+mul)+add:
-//   u[i][o] = sum_c (one_plus + mul[i][c]) W[o][c],   v[i][o] = sum_c add[i][c] W[o][c] + bias[o].
-// One warp per output column: its weight row stays in registers across the table rows.
-__global__ void __launch_bounds__(256)
-ln_fold_kernel(const __half* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ mul, const float* __restrict__ add, int row_stride,
-               float one_plus, int n, int O, float* __restrict__ u, float* __restrict__ v, int out_stride) {
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (o >= O) return;
-    constexpr int PER = D / 32;
-    float w[PER];
-    const __half* wr = W + (size_t)o * D;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) w[i] = __half2float(wr[lane + 32 * i]);
-    const float b = bias ? bias[o] : 0.f;
-    for (int i = 0; i < n; ++i) {
-        const float* m = mul + (size_t)i * row_stride;
-        const float* a = add + (size_t)i * row_stride;
-        float su = 0.f, sv = 0.f;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) { su = fmaf(w[j], one_plus + m[lane + 32 * j], su); sv = fmaf(w[j], a[lane + 32 * j], sv); }
-#pragma unroll
-        for (int s2 = 16; s2; s2 >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, s2); sv += __shfl_xor_sync(0xffffffffu, sv, s2); }
-        if (lane == 0) { u[(size_t)i * out_stride + o] = su; v[(size_t)i * out_stride + o] = sv + b; }
-    }
-}
-
 // Warp per token: v = y2 . W4^T (3 outputs), then the Euler update of sampler.py:88-90.
 __global__ void __launch_bounds__(256)
 head_final_kernel(const __half* __restrict__ y2, const float* __restrict__ W4, int T, float* __restrict__ v_out,
@@ -258,14 +232,6 @@ int launch_ada_linear(const __half* W, const float* b, const float* in, int in_h
     if (K == 256) ada_linear_kernel<256><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
     else if (K == 512) ada_linear_kernel<512><<<grid, 256, 0, st>>>(W, b, in, in_has_m, out, n, M, O, silu_out);
     else return fail(RAP_EINVAL, "ada_linear: unsupported K=%d", K);
-    RAP_CUDA(cudaGetLastError());
-    note_launch();
-    return RAP_OK;
-}
-int launch_ln_fold(const __half* W, const float* bias, const float* mul, const float* add, int row_stride, float one_plus, int n, int O,
-                   float* u, float* v, int out_stride, cudaStream_t st) {
-    ProfScope _ps(KC_ADA, st);
-    ln_fold_kernel<<<ceil_div(O, 8), 256, 0, st>>>(W, bias, mul, add, row_stride, one_plus, n, O, u, v, out_stride);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;

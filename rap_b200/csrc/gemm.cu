@@ -207,18 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(tfull_bar(acc), acc_phase, 0x31);
                 tc_fence_after();
                 if (dbg_w) GEMM_TS(6);
-                const bool extras = p.table != nullptr;      // anchor-row select: only the once-per-scene static embedding GEMM
-                // LN folding (gemm.cuh): fp16 operand of the next GEMM = v * (1 + scale of the next LN), and per-row partial moments
-                __half* o16_base = p.out16 ? p.out16 + (size_t)(row_base + rr0) * p.ld16 + col0 + cc * 4 : nullptr;
-                const size_t pitch4_16 = (size_t)4 * p.ld16;
-                const float* mul_base = nullptr;             // this lane's 4 columns of the (single or per-row) scale table
-                int tab_row[8];
-#pragma unroll
-                for (int it = 0; it < 8; ++it) tab_row[it] = (p.ln_mul && 4 * it < rows_left) ? p.ln_row_of_tok[row_base + rr0 + 4 * it] : 0;
-                if (p.ln_mul) mul_base = p.ln_mul + col0 + cc * 4;
-                float s1[8], s2[8];
-#pragma unroll
-                for (int it = 0; it < 8; ++it) { s1[it] = 0.f; s2[it] = 0.f; }
+                const bool extras = p.table || p.out16;      // anchor-row select (embedding GEMM) / fp16 shadow (last FF2): rare launches
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     tmem_ld32(t_row + half * HC + c * 32, r);
@@ -234,20 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float4 a = ad[c & 1][it];
                             const float4 v = make_float4(__uint_as_float(u.x) + a.x + b.x, __uint_as_float(u.y) + a.y + b.y,
                                                          __uint_as_float(u.z) + a.z + b.z, __uint_as_float(u.w) + a.w + b.w);
-                            if (4 * it < rows_left) {
-                                *reinterpret_cast<float4*>(out_base + it * pitch4 + c * 32) = v;
-                                if (o16_base) {
-                                    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-                                    if (mul_base) {
-                                        const float4 t = *reinterpret_cast<const float4*>(mul_base + (size_t)tab_row[it] * p.ln_row_stride + c * 32);
-                                        m = make_float4(p.ln_one_plus + t.x, p.ln_one_plus + t.y, p.ln_one_plus + t.z, p.ln_one_plus + t.w);
-                                    }
-                                    *reinterpret_cast<uint2*>(o16_base + it * pitch4_16 + c * 32) =
-                                        make_uint2(pack_half2(v.x * m.x, v.y * m.y), pack_half2(v.z * m.z, v.w * m.w));
-                                }
-                                s1[it] += (v.x + v.y) + (v.z + v.w);
-                                s2[it] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                            }
+                            if (4 * it < rows_left) *reinterpret_cast<float4*>(out_base + it * pitch4 + c * 32) = v;
                         }
                     } else {
                         const int col = col0 + c * 32 + cc * 4;
@@ -271,47 +247,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (c + 2 < NCH) load_addend(ad[c & 1], c + 2);
                     __syncwarp();
                 }
-                if (p.ln_stats_out) {                        // the 8 lanes that share a row add up their column groups
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-#pragma unroll
-                        for (int o = 1; o < 8; o <<= 1) { s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o); s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o); }
-                        if (cc == 0 && 4 * it < rows_left)
-                            *reinterpret_cast<float2*>(p.ln_stats_out + ((size_t)(row_base + rr0 + 4 * it) * p.ln_nslice + col0 / HC) * 2) = make_float2(s1[it], s2[it]);
-                    }
-                }
             } else {
                 // fp16 outputs: each staging round holds 64 output columns (128 B per row).
                 mbar_wait(tfull_bar(acc), acc_phase, 0x31);
                 tc_fence_after();
                 if (dbg_w) GEMM_TS(6);
                 constexpr int ROUNDS = (EPI == EPI_GEGLU) ? 1 : HC / 64;    // GEGLU: 2 x (32 h + 32 g) -> 64 outputs per warp
-                // LN folding, consumer side (gemm.cuh): this thread's row statistics and its table row of u / v
-                float ln_mu = 0.f, ln_rstd = 1.f;
-                const float *ln_urow = nullptr, *ln_vrow = nullptr;
-                if (p.ln_stats) {
-                    const int row_t = min(row_base + lane, p.M - 1);
-                    const float2* part = reinterpret_cast<const float2*>(p.ln_stats + (size_t)row_t * p.ln_nslice * 2);
-                    float a1 = 0.f, a2 = 0.f;
-                    for (int sl = 0; sl < p.ln_nslice; ++sl) { const float2 v = part[sl]; a1 += v.x; a2 += v.y; }
-                    const float inv_k = 1.0f / (float)p.K;
-                    ln_mu = a1 * inv_k;
-                    ln_rstd = rsqrtf(fmaxf(a2 * inv_k - ln_mu * ln_mu, 0.f) + 1e-5f);     // biased variance, eps like nn.LayerNorm
-                    const size_t tab = (size_t)p.ln_row_of_tok[row_t] * p.ln_uv_stride;
-                    ln_urow = p.ln_u + tab;
-                    ln_vrow = p.ln_v + tab;
-                }
-                // y = rstd * (acc - mu * u_n) + v_n for 32 consecutive columns starting at `col`
-                auto ln_apply = [&](uint32_t (&acc32)[32], int col) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 u4 = *reinterpret_cast<const float4*>(ln_urow + col + i), v4 = *reinterpret_cast<const float4*>(ln_vrow + col + i);
-                        acc32[i] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mu, u4.x, __uint_as_float(acc32[i])), v4.x));
-                        acc32[i + 1] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mu, u4.y, __uint_as_float(acc32[i + 1])), v4.y));
-                        acc32[i + 2] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mu, u4.z, __uint_as_float(acc32[i + 2])), v4.z));
-                        acc32[i + 3] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mu, u4.w, __uint_as_float(acc32[i + 3])), v4.w));
-                    }
-                };
 #pragma unroll 1
                 for (int rd = 0; rd < ROUNDS; ++rd) {
                     uint32_t r2[32];
@@ -344,7 +285,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tmem_ld32(t_row + hc * 64, r);
                         tmem_ld32(t_row + hc * 64 + 32, r2);
                         tmem_ld_wait();
-                        if (ln_urow) { ln_apply(r, col); ln_apply(r2, col + 32); }
                         if (section < 2) {
                             float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -374,13 +314,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tmem_ld32(t_row + c * 32, r);              // h part
                             tmem_ld32(t_row + BN / 2 + c * 32, r2);    // g part
                             tmem_ld_wait();
-                            if (ln_urow) { ln_apply(r, n0 + c * 32); ln_apply(r2, n0 + BN / 2 + c * 32); }      // v_n carries the bias
                             const float* bh = p.bias + n0 + c * 32;
                             const float* bg = p.bias + n0 + BN / 2 + c * 32;
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float4 h4 = ln_urow ? z4 : *reinterpret_cast<const float4*>(bh + i), g4 = ln_urow ? z4 : *reinterpret_cast<const float4*>(bg + i);
+                                const float4 h4 = *reinterpret_cast<const float4*>(bh + i), g4 = *reinterpret_cast<const float4*>(bg + i);
                                 pk[cp * 16 + i / 2] = pack_half2((__uint_as_float(r[i]) + h4.x) * gelu_erf(__uint_as_float(r2[i]) + g4.x),
                                                                  (__uint_as_float(r[i + 1]) + h4.y) * gelu_erf(__uint_as_float(r2[i + 1]) + g4.y));
                                 pk[cp * 16 + i / 2 + 1] = pack_half2((__uint_as_float(r[i + 2]) + h4.z) * gelu_erf(__uint_as_float(r2[i + 2]) + g4.z),

@@ -27,19 +27,6 @@ struct GemmArgs {
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
-    // LayerNorm folded around the GEMMs (DESIGN.md "LN folding"): LN(x)(1+s)+t feeding a GEMM is  rstd*(x(1+s)) W^T - rstd*mu*u + v  with
-    // u = W(1+s), v = W t + b.  The PRODUCER of x (EPI_F32) writes the fp16 operand x*(1+s) of the NEXT GEMM and per-row partial sums;
-    // the CONSUMER (EPI_QKV / EPI_GEGLU) applies rstd, mu, u, v in its epilogue.  No LayerNorm kernel, no extra pass over x.
-    const float* ln_mul;      // producer: scale table of the next LN [table rows][ln_row_stride] (null: shadow = x)
-    const int* ln_row_of_tok; // producer + consumer: table row of every token (never null when ln_mul / ln_u is set)
-    int ln_row_stride;        // producer: floats between table rows of ln_mul
-    float ln_one_plus;        // producer: 1 for AdaLN (x (1 + scale)), 0 for the affine ff_norm (x * weight)
-    float* ln_stats_out;      // producer: [M][ln_nslice][2] partial (sum, sum of squares) over this warp's columns, or null
-    const float* ln_stats;    // consumer: the partials of its A rows (null: A is used as is, bias path)
-    int ln_nslice;            // partials per row
-    const float* ln_u;        // consumer: [table rows][ln_uv_stride] u_n
-    const float* ln_v;        // consumer: [table rows][ln_uv_stride] v_n (bias included)
-    int ln_uv_stride;
 };
 
 int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t st);

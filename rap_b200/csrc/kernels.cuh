@@ -22,10 +22,6 @@ int launch_timestep_sincos(const float* t, float* out, int n, cudaStream_t st); 
 int launch_ada_linear(const __half* W, const float* b, const float* in, int in_has_m, float* out, int n, int M, int O, int K,
                       int silu_out, cudaStream_t st);
 
-// LN folding tables (gemm.cuh): u[i][o] = sum_c (one_plus + mul[i][c]) W[o][c], v[i][o] = sum_c add[i][c] W[o][c] + bias[o]; W is [O,512] fp16
-int launch_ln_fold(const __half* W, const float* bias, const float* mul, const float* add, int row_stride, float one_plus, int n, int O,
-                   float* u, float* v, int out_stride, cudaStream_t st);
-
 // ---- head tail + Euler step (point_cloud_dit.py:116 last Linear; sampler.py:88-90) --------------
 // v = y2[T,256] . W4[3,256]^T.  If x_t != null: x0_hat = x_t - v t ; x_t <- x_t - dt v (written to x_t and xt_traj).
 int launch_head_final(const __half* y2, const float* W4, int T, float* v_out, float* x_t, float t, float dt,
