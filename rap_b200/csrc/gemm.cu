@@ -114,7 +114,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (leader) {
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     if (!b_done) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+                    int a_col = kb * BK, a_row = m0;
+                    if (p.conv_pitch) {                          // implicit 3x3 convolution: shifted box of the halo-padded activation map
+                        const int tap = kb / p.conv_chunks;
+                        a_col = (kb - tap * p.conv_chunks) * BK;
+                        a_row = m0 + (tap / 3 - 1) * p.conv_pitch + (tap % 3 - 1);
+                    }
+                    tma_load_2d(sa, &tmA, full_bar(stage), a_col, a_row);
                     if (!b_done) tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -333,10 +339,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         __half* dst = p.out16 + (size_t)(row_base + rr0) * p.ld16 + out_col + cc * 8;   // hoisted: the loop adds 4-row pitches
                         const size_t pitch4 = (size_t)4 * p.ld16;
                         const int rows_left = p.M - (row_base + rr0);
+                        if (!p.conv_pitch) {
 #pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
-                            if (4 * it < rows_left) *reinterpret_cast<uint4*>(dst + it * pitch4) = u;
+                            for (int it = 0; it < 8; ++it) {
+                                const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
+                                if (4 * it < rows_left) *reinterpret_cast<uint4*>(dst + it * pitch4) = u;
+                            }
+                        } else {                                 // convolution map: real positions only, plus the circular halo copies
+                            const ptrdiff_t wrap = (ptrdiff_t)p.conv_w * p.ld16;
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const uint4 u = lds4(stg_r + it * 4 * STG_ROW_BYTES);
+                                const int pos = (row_base + rr0 + 4 * it) % p.conv_rows, e = pos / p.conv_pitch, a = pos - e * p.conv_pitch;
+                                if (4 * it < rows_left && e < p.conv_h && a >= 1 && a <= p.conv_w) {
+                                    *reinterpret_cast<uint4*>(dst + it * pitch4) = u;
+                                    if (a == p.conv_w) *reinterpret_cast<uint4*>(dst + it * pitch4 - wrap) = u;      // column 0 = last real column
+                                    if (a == 1) *reinterpret_cast<uint4*>(dst + it * pitch4 + wrap) = u;             // column w+1 = first real column
+                                }
+                            }
                         }
                     }
                     __syncwarp();

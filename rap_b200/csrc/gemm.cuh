@@ -27,6 +27,12 @@ struct GemmArgs {
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
+    // Implicit 3x3 convolution (spinnet.cu): A is an activation map stored per item as (conv_h + 1) rows x conv_pitch = conv_w + 2 columns
+    // of positions (azimuth halo columns hold the circular neighbours, the extra row is an all-zero separator = elevation padding of
+    // this and the next item), so tap (de, da) of an output tile is the SAME 2-D TMA box shifted by de * conv_pitch + da rows: no im2col
+    // operand exists.  k-block kb = tap * conv_chunks + 64-channel chunk.  The fp16 epilogue writes only real positions (+ their halo
+    // copies), so separators stay zero.  conv_pitch = 0: plain GEMM.
+    int conv_pitch, conv_rows, conv_h, conv_w, conv_chunks;
 };
 
 int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, cudaStream_t st);

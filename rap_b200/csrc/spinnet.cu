@@ -7,9 +7,11 @@
 //                              de-rotation, 1x1 conv 3->16 + BN + ReLU, max over the 10 samples   (patch_embedder.py:168-183,74-76;
 //                              utils/common.py:396-469).  The (K,420,10,3) tensor the reference materialises (206 MB per view) never
 //                              leaves the SM.
-//   im2col_kernel + tcgen05 GEMM (gemm.cu, bias+ReLU epilogue)  the cylindrical CNN: Conv3d 16->64 (radial 3->1) and 7 x Conv2d 3x3 with
-//                              circular azimuth / zero elevation padding done by ADDRESSING instead of torch.cat (patchnet.py:49-84,
-//                              utils/common.py:230-275); BatchNorm (eval, no affine) folded into weights and bias.
+//   tcgen05 GEMM as IMPLICIT convolution (gemm.cu/gemm.cuh conv_* arguments, bias+ReLU epilogue)  the cylindrical CNN: Conv3d 16->64 (radial
+//                              3->1) and 7 x Conv2d 3x3.  Maps are stored halo-padded per keypoint (8 x 22 positions: circular azimuth
+//                              neighbours in the halo columns, one zero separator row = elevation padding), so each of the 9 taps is the
+//                              same TMA box shifted by a constant number of rows -- no im2col operand (the first version wrote and re-read
+//                              6 GB of it per view) (patchnet.py:49-84, utils/common.py:230-275); BatchNorm folded into weights / bias.
 //   pool_kernel          C2    attention pooling (two 1x1 convs + BN + ReLU), weighted mean over 7x20, L2 norm  (patch_embedder.py:78-80)
 #include "../../include/rap_b200.h"
 #include "gemm.cuh"
@@ -25,6 +27,8 @@ namespace rap {
 namespace {
 
 constexpr int PATCH = 512, NVOX = 420, RAD = 3, ELE = 7, AZI = 20, NSAMP = 10, POS = ELE * AZI;   // 140 output positions per keypoint
+// Activation maps are stored halo-padded: per keypoint (ELE + 1) rows of PITCH = AZI + 2 positions (gemm.cuh, implicit convolution)
+constexpr int PITCH = AZI + 2, KROWS = (ELE + 1) * PITCH;                                         // 22, 176
 
 __constant__ float c_vox[NVOX * 3];       // voxel centres, order (rad, ele, azi)
 __constant__ float c_rot[AZI * 2];        // cos / sin of -a * 18 deg
@@ -92,7 +96,7 @@ patch_kernel(const float* __restrict__ pts /* shuffled (N,3) */, const float* __
 // ---------------------------------------------------------------------------------------------------------------- X3 + first conv
 // Block = one keypoint (patch in shared memory), thread = one spherical voxel.
 __global__ void __launch_bounds__(448)
-voxel_feature_kernel(const float* __restrict__ patches, int K, __half* __restrict__ feat /* (K,420,16) channels-last */) {
+voxel_feature_kernel(const float* __restrict__ patches, int K, __half* __restrict__ feat /* (K*176, 64) halo-padded map */) {
     __shared__ float sp[PATCH * 3];
     const int k = blockIdx.x;
     for (int i = threadIdx.x; i < PATCH * 3; i += blockDim.x) sp[i] = patches[(size_t)k * PATCH * 3 + i];
@@ -131,47 +135,34 @@ voxel_feature_kernel(const float* __restrict__ patches, int K, __half* __restric
             best[o] = fmaxf(best[o], t);                           // max(relu(.)) == max(0, .)
         }
     }
-    uint4* dst = reinterpret_cast<uint4*>(feat + ((size_t)k * NVOX + v) * 16);
+    // position (ele, azi) of the padded map, channels [rad*16, rad*16+16) of 64 (48 used: the radial axis is the Conv3d's depth, which
+    // its 3-deep kernel collapses, so it folds into the channel dimension); azimuth 0 / 19 also fill the circular halo columns
+    const int rad = v / POS, e = (v / AZI) % ELE;
     __half2 h[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) h[o] = __floats2half2_rn(best[2 * o], best[2 * o + 1]);
-    dst[0] = *reinterpret_cast<uint4*>(&h[0]);
-    dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+    __half* row = feat + ((size_t)k * KROWS + e * PITCH + a + 1) * 64 + rad * 16;
+    auto put = [&](__half* d) { reinterpret_cast<uint4*>(d)[0] = *reinterpret_cast<uint4*>(&h[0]); reinterpret_cast<uint4*>(d)[1] = *reinterpret_cast<uint4*>(&h[4]); };
+    put(row);
+    if (a == AZI - 1) put(row - AZI * 64);
+    if (a == 0) put(row + AZI * 64);
 }
 
-// ---------------------------------------------------------------------------------------------------------------- im2col
-// A[k*140 + e*20 + a][tap*C + c] = in[k][d=kd][e+ke-1][(a+ka-1) mod 20][c]  (zero outside the elevation range, zero K padding).
-// One thread per 16-byte (8-channel) chunk.
-__global__ void im2col_kernel(const __half* __restrict__ in, int ld_in, int D, int C, int Kp, int n_kp, __half* __restrict__ A) {
-    const int chunks_per_row = Kp / 8;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n_kp * POS * chunks_per_row;
-    if (idx >= total) return;
-    const int ch = (int)(idx % chunks_per_row);
-    const size_t row = idx / chunks_per_row;
-    const int pos = (int)(row % POS), k = (int)(row / POS);
-    const int e = pos / AZI, a = pos % AZI;
-    const int col = ch * 8, tap = col / C, c = col % C;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (tap < D * 9) {
-        const int kd = tap / 9, ke = (tap / 3) % 3, ka = tap % 3;
-        const int se = e + ke - 1, sa = (a + ka - 1 + AZI) % AZI;
-        if (se >= 0 && se < ELE) v = *reinterpret_cast<const uint4*>(in + ((((size_t)k * D + kd) * ELE + se) * AZI + sa) * ld_in + c);
-    }
-    *reinterpret_cast<uint4*>(A + row * Kp + col) = v;
-}
-
-// out Wp[128][Kp] fp16 = W[co][ci][taps] / sqrt(var+eps) re-ordered to [co][tap][ci]; bp[128] fp32 = (b - mean) / sqrt(var+eps)
+// ---------------------------------------------------------------------------------------------------------------- weights
+// out Wp[128][9 * cpad] fp16 = W / sqrt(var+eps) re-ordered to [co][tap(ke,ka)][input channel, padded to cpad]; bp[128] fp32 = (b - mean) / sqrt(var+eps).
+// Conv3d (taps = 27, source [co][ci][kd][ke][ka]): the depth index joins the channel, input channel = kd * Cin + ci.
 __global__ void fold_conv_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ var,
-                                 int Cout, int Cin, int taps, int Kp, __half* __restrict__ Wp, float* __restrict__ bp) {
+                                 int Cout, int Cin, int taps, int cpad, __half* __restrict__ Wp, float* __restrict__ bp) {
+    const int Kp = 9 * cpad;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128 * Kp) return;
     const int co = idx / Kp, col = idx % Kp;
+    const int tap = col / cpad, ch = col % cpad, depth = taps / 9;
     float v = 0.f;
     const float inv = (co < Cout && var) ? rsqrtf(var[co] + 1e-5f) : 1.0f;
-    if (co < Cout && col < taps * Cin) {
-        const int tap = col / Cin, ci = col % Cin;
-        v = W[((size_t)co * Cin + ci) * taps + tap] * inv;
+    if (co < Cout && ch < depth * Cin) {
+        const int kd = ch / Cin, ci = ch % Cin;
+        v = W[((size_t)co * Cin + ci) * taps + kd * 9 + tap] * inv;
     }
     Wp[idx] = __float2half_rn(v);
     if (col == 0) bp[co] = co < Cout ? (b[co] - (mean ? mean[co] : 0.f)) * inv : 0.f;
@@ -184,7 +175,7 @@ __constant__ PoolW c_pool;
 // One warp per keypoint, lane = output position (140 positions -> 5 rounds): every lane holds its position's 32 channels in registers, the
 // two 1x1 convs run as register dot products against weights broadcast from constant memory, and only the final 32 channel sums cross
 // lanes (through a padded shared-memory transpose).  The first version put the channel on the lane and paid 16 five-step shuffle
-// reductions per position (1.2 ms per 2048 keypoints, a third of the extractor).  x: (K*140, ld) fp32 rows, first 32 columns valid.
+// reductions per position (1.2 ms per 2048 keypoints, a third of the extractor).  x: halo-padded map (K*176, ld) fp32, first 32 columns valid.
 __global__ void __launch_bounds__(128)
 pool_kernel(const float* __restrict__ x, int ld, int K, float* __restrict__ desc) {
     __shared__ float part[4][32][33];
@@ -195,7 +186,7 @@ pool_kernel(const float* __restrict__ x, int ld, int K, float* __restrict__ desc
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
     for (int p = lane; p < POS; p += 32) {
-        const float4* row = reinterpret_cast<const float4*>(x + ((size_t)k * POS + p) * ld);
+        const float4* row = reinterpret_cast<const float4*>(x + ((size_t)k * KROWS + (p / AZI) * PITCH + p % AZI + 1) * ld);
         float xv[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) { const float4 v = row[q]; xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w; }
@@ -224,7 +215,7 @@ pool_kernel(const float* __restrict__ x, int ld, int K, float* __restrict__ desc
     desc[(size_t)k * 32 + lane] = sum / fmaxf(sqrtf(n2), 1e-12f);
 }
 
-struct Layer { int Cin, Cout, taps, D, Kp; std::string w, b, bn; __half* Wp; float* bp; CUtensorMap tmB; };
+struct Layer { int Cin, Cout, taps, D, cpad, Kp; std::string w, b, bn; __half* Wp; float* bp; CUtensorMap tmB; };
 
 }  // namespace
 }  // namespace rap
@@ -244,7 +235,7 @@ struct rap_spinnet {
 };
 
 namespace {
-const int kChunk = 2048;   // keypoints per pass (bounds the im2col operand to 660 MB)
+const int kChunk = 2048;   // keypoints per pass (activation maps: 2048 * 176 rows)
 
 void spec(rap_spinnet* h) {
     auto add = [&](const std::string& k, int64_t n) { h->expect[k] = n; };
@@ -260,7 +251,7 @@ void spec(rap_spinnet* h) {
         const std::string p = "conv_net.ops." + std::to_string(c[0]) + ".";
         add(p + "weight", (int64_t)c[2] * c[1] * c[3]); add(p + "bias", c[2]);
         Layer L{};
-        L.Cin = c[1]; L.Cout = c[2]; L.taps = c[3]; L.D = c[3] == 27 ? 3 : 1; L.Kp = ((c[1] * c[3] + 63) / 64) * 64;
+        L.Cin = c[1]; L.Cout = c[2]; L.taps = c[3]; L.D = c[3] == 27 ? 3 : 1; L.cpad = ((c[1] * L.D + 63) / 64) * 64; L.Kp = 9 * L.cpad;
         L.w = p + "weight"; L.b = p + "bias";
         if (c[0] != 21) { L.bn = "conv_net.ops." + std::to_string(c[0] + 1) + "."; bn(L.bn, c[2], false); }
         h->layers.push_back(L);
@@ -359,7 +350,7 @@ extern "C" int rap_spinnet_finalize(rap_spinnet_t* h) {
     for (auto& L : h->layers) {
         const float* mean = L.bn.empty() ? nullptr : h->raw[L.bn + "running_mean"];
         const float* var = L.bn.empty() ? nullptr : h->raw[L.bn + "running_var"];
-        fold_conv_kernel<<<ceil_div(128 * L.Kp, 256), 256>>>(h->raw[L.w], h->raw[L.b], mean, var, L.Cout, L.Cin, L.taps, L.Kp, L.Wp, L.bp);
+        fold_conv_kernel<<<ceil_div(128 * L.Kp, 256), 256>>>(h->raw[L.w], h->raw[L.b], mean, var, L.Cout, L.Cin, L.taps, L.cpad, L.Wp, L.bp);
         RAP_CUDA(cudaGetLastError());
         RAP_TRY(make_tmap_f16_sw128(&L.tmB, L.Wp, 128, L.Kp, L.Kp, 128));
     }
@@ -379,18 +370,18 @@ extern "C" int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_
         RAP_CUDA(cudaStreamSynchronize(st));
         cudaFree(h->ws);
         h->ws = nullptr;
-        const size_t rows = (size_t)chunk * POS;
-        h->ws_bytes = (size_t)n_points * 12 + (size_t)chunk * PATCH * 12 + (size_t)chunk * NVOX * 16 * 2 + rows * 1152 * 2 + 2 * rows * 128 * 2 + rows * 128 * 4 + 8192;
+        const size_t rows = (size_t)chunk * KROWS;
+        h->ws_bytes = (size_t)n_points * 12 + (size_t)chunk * PATCH * 12 + rows * 64 * 2 + 2 * rows * 128 * 2 + rows * 128 * 4 + 8192;
         if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { h->ws_chunk = h->ws_points = 0; return fail(RAP_ENOMEM, "rap_spinnet_extract: cudaMalloc(%zu) failed", h->ws_bytes); }
+        RAP_CUDA(cudaMemsetAsync(h->ws, 0, h->ws_bytes, st));       // separator rows / padded channels of the maps are never written again
         h->ws_chunk = chunk; h->ws_points = n_points;
     }
     char* p = h->ws;
     auto take = [&](size_t n) { char* q = p; p += (n + 255) / 256 * 256; return q; };
-    const size_t rows_cap = (size_t)h->ws_chunk * POS;
+    const size_t rows_cap = (size_t)h->ws_chunk * KROWS;
     float* pts_s = reinterpret_cast<float*>(take((size_t)h->ws_points * 12));
     float* patches = reinterpret_cast<float*>(take((size_t)h->ws_chunk * PATCH * 12));
-    __half* feat0 = reinterpret_cast<__half*>(take((size_t)h->ws_chunk * NVOX * 16 * 2));
-    __half* A = reinterpret_cast<__half*>(take(rows_cap * 1152 * 2));
+    __half* feat0 = reinterpret_cast<__half*>(take(rows_cap * 64 * 2));
     __half* fm[2] = {reinterpret_cast<__half*>(take(rows_cap * 128 * 2)), reinterpret_cast<__half*>(take(rows_cap * 128 * 2))};
     float* out32 = reinterpret_cast<float*>(take(rows_cap * 128 * 4));
 
@@ -398,24 +389,21 @@ extern "C" int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_
     RAP_CUDA(cudaGetLastError());
     for (int k0 = 0; k0 < n_keypoints; k0 += chunk) {
         const int kc = n_keypoints - k0 < chunk ? n_keypoints - k0 : chunk;
-        const int M = kc * POS;
+        const int M = kc * KROWS;
         patch_kernel<<<ceil_div(kc, 8), 256, 0, st>>>(pts_s, keypoints + (size_t)k0 * 3, n_points, kc, des_r, patches);
         RAP_CUDA(cudaGetLastError());
         voxel_feature_kernel<<<kc, 448, 0, st>>>(patches, kc, feat0);
         RAP_CUDA(cudaGetLastError());
         note_launch(2);
         const __half* in = feat0;
-        int ld_in = 16;
+        int ld_in = 64;
         for (size_t li = 0; li < h->layers.size(); ++li) {
             Layer& L = h->layers[li];
-            const size_t total = (size_t)M * (L.Kp / 8);
-            im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, ld_in, L.D, L.Cin, L.Kp, kc, A);
-            RAP_CUDA(cudaGetLastError());
-            note_launch();
-            CUtensorMap tmA;
-            RAP_TRY(make_tmap_f16_sw128(&tmA, A, M, L.Kp, L.Kp, 128));
+            CUtensorMap tmA;                                     // the activation map itself: every tap is a shifted box of it
+            RAP_TRY(make_tmap_f16_sw128(&tmA, in, M, ld_in, ld_in, 128));
             GemmArgs g{};
             g.M = M; g.N = 128; g.K = L.Kp; g.bias = L.bp;
+            g.conv_pitch = PITCH; g.conv_rows = KROWS; g.conv_h = ELE; g.conv_w = AZI; g.conv_chunks = L.cpad / 64;
             const bool last = li + 1 == h->layers.size();
             if (last) { g.out32 = out32; g.ld32 = 128; RAP_TRY(launch_gemm(EPI_F32, 128, tmA, L.tmB, g, st)); }
             else { g.out16 = fm[li & 1]; g.ld16 = 128; g.act = 1; RAP_TRY(launch_gemm(EPI_F16_SILU, 128, tmA, L.tmB, g, st)); }
