@@ -42,11 +42,14 @@ __global__ void gather_points_kernel(const float* __restrict__ pts, const int* _
     out[3 * i] = pts[3 * s]; out[3 * i + 1] = pts[3 * s + 1]; out[3 * i + 2] = pts[3 * s + 2];
 }
 
-// One warp per keypoint, 8 keypoints per block share every 256-point tile staged in shared memory (coalesced loads of xyz).
+// One warp per keypoint, 8 keypoints per block share every 512-point tile of the cloud; tiles are double-buffered with cp.async so the
+// next tile's 6 KB arrive under the current tile's distance tests (the single-buffered version spent most of its 384 us per 2048 keypoints
+// waiting on one L2 round trip per tile).
+constexpr int kTilePts = 512;
 __global__ void __launch_bounds__(256)
 patch_kernel(const float* __restrict__ pts /* shuffled (N,3) */, const float* __restrict__ kpts, int N, int K, float des_r,
-             float* __restrict__ patches /* (K,512,3) */) {
-    __shared__ float tile[256 * 3];
+             float* __restrict__ patches /* (K,512,3) */, int* __restrict__ n_real /* (K) neighbours found, <= 512; may be null */) {
+    __shared__ __align__(16) float tile[2][kTilePts * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + warp;
     const bool active = k < K;
@@ -54,19 +57,35 @@ patch_kernel(const float* __restrict__ pts /* shuffled (N,3) */, const float* __
     if (active) { kx = kpts[3 * k]; ky = kpts[3 * k + 1]; kz = kpts[3 * k + 2]; }
     const float r2 = des_r * des_r;
     float* out = patches + (size_t)(active ? k : 0) * PATCH * 3;
+    auto fetch = [&](int buf, int base) {                 // tile base is a multiple of 512 points = 6144 bytes: 16-byte aligned chunks
+        const int floats = min(kTilePts, N - base) * 3;
+        const float* src = pts + (size_t)base * 3;
+        for (int i = threadIdx.x * 4; i < floats; i += 256 * 4) {
+            if (i + 4 <= floats) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[buf][i]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
+            } else {
+                for (int j = i; j < floats; ++j) tile[buf][j] = src[j];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int count = 0;
-    for (int base = 0; base < N; base += 256) {
-        const int n_tile = min(256, N - base);
+    fetch(0, 0);
+    for (int base = 0, buf = 0; base < N; base += kTilePts, buf ^= 1) {
+        const int n_tile = min(kTilePts, N - base);
+        const bool more = base + kTilePts < N;
+        if (more) fetch(buf ^ 1, base + kTilePts);
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        for (int i = threadIdx.x; i < n_tile * 3; i += 256) tile[i] = pts[(size_t)base * 3 + i];
-        __syncthreads();
+        const float* tl = tile[buf];
         if (active && count < PATCH) {
             for (int j = 0; j < n_tile; j += 32) {
                 const int i = j + lane;
                 float px = 0, py = 0, pz = 0;
                 bool in = false;
                 if (i < n_tile) {
-                    px = tile[3 * i]; py = tile[3 * i + 1]; pz = tile[3 * i + 2];
+                    px = tl[3 * i]; py = tl[3 * i + 1]; pz = tl[3 * i + 2];
                     const float dx = kx - px, dy = ky - py, dz = kz - pz;
                     in = dx * dx + dy * dy + dz * dz < r2;                     // strict <, like pytorch3d
                 }
@@ -77,10 +96,12 @@ patch_kernel(const float* __restrict__ pts /* shuffled (N,3) */, const float* __
                 if (count >= PATCH) break;
             }
         }
-        if (__syncthreads_and(!active || count >= PATCH)) break;
+        if (__syncthreads_and(!active || count >= PATCH)) break;      // also orders this tile's reads before its buffer is refilled
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (!active) return;
     count = min(count, PATCH);
+    if (n_real && lane == 0) n_real[k] = count;
     __syncwarp();
     // centre = last slot: the 512th neighbour if the patch is full, else the keypoint (patch_embedder.py:142 + :122-131)
     float cx = kx, cy = ky, cz = kz;
@@ -96,10 +117,14 @@ patch_kernel(const float* __restrict__ pts /* shuffled (N,3) */, const float* __
 // ---------------------------------------------------------------------------------------------------------------- X3 + first conv
 // Block = one keypoint (patch in shared memory), thread = one spherical voxel.
 __global__ void __launch_bounds__(448)
-voxel_feature_kernel(const float* __restrict__ patches, int K, __half* __restrict__ feat /* (K*176, 64) halo-padded map */) {
+voxel_feature_kernel(const float* __restrict__ patches, const int* __restrict__ n_real, int K,
+                     __half* __restrict__ feat /* (K*176, 64) halo-padded map */) {
     __shared__ float sp[PATCH * 3];
     const int k = blockIdx.x;
-    for (int i = threadIdx.x; i < PATCH * 3; i += blockDim.x) sp[i] = patches[(size_t)k * PATCH * 3 + i];
+    // Slots behind the real neighbours of a non-full patch are copies of the keypoint = exactly (0,0,0) after centring: as samples they
+    // are indistinguishable from the zero padding below, so only the real neighbours need to be scanned (typically 100-300 of 512).
+    const int n_pts = n_real[k];
+    for (int i = threadIdx.x; i < n_pts * 3; i += blockDim.x) sp[i] = patches[(size_t)k * PATCH * 3 + i];
     __syncthreads();
     const int v = threadIdx.x;
     if (v >= NVOX) return;
@@ -109,7 +134,7 @@ voxel_feature_kernel(const float* __restrict__ patches, int K, __half* __restric
 #pragma unroll
     for (int s = 0; s < NSAMP; ++s) gx[s] = gy[s] = gz[s] = 0.f;
     int cnt = 0, first = -1;
-    for (int i = 0; i < PATCH && cnt < NSAMP; ++i) {
+    for (int i = 0; i < n_pts && cnt < NSAMP; ++i) {
         const float px = sp[3 * i], py = sp[3 * i + 1], pz = sp[3 * i + 2];
         const float dx = cx - px, dy = cy - py, dz = cz - pz;
         if (dx * dx + dy * dy + dz * dz < r2) {
@@ -371,7 +396,7 @@ extern "C" int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_
         cudaFree(h->ws);
         h->ws = nullptr;
         const size_t rows = (size_t)chunk * KROWS;
-        h->ws_bytes = (size_t)n_points * 12 + (size_t)chunk * PATCH * 12 + rows * 64 * 2 + 2 * rows * 128 * 2 + rows * 128 * 4 + 8192;
+        h->ws_bytes = (size_t)n_points * 12 + (size_t)chunk * PATCH * 12 + (size_t)chunk * 4 + 256 + rows * 64 * 2 + 2 * rows * 128 * 2 + rows * 128 * 4 + 8192;
         if (cudaMalloc(&h->ws, h->ws_bytes) != cudaSuccess) { h->ws_chunk = h->ws_points = 0; return fail(RAP_ENOMEM, "rap_spinnet_extract: cudaMalloc(%zu) failed", h->ws_bytes); }
         RAP_CUDA(cudaMemsetAsync(h->ws, 0, h->ws_bytes, st));       // separator rows / padded channels of the maps are never written again
         h->ws_chunk = chunk; h->ws_points = n_points;
@@ -381,6 +406,7 @@ extern "C" int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_
     const size_t rows_cap = (size_t)h->ws_chunk * KROWS;
     float* pts_s = reinterpret_cast<float*>(take((size_t)h->ws_points * 12));
     float* patches = reinterpret_cast<float*>(take((size_t)h->ws_chunk * PATCH * 12));
+    int* n_real = reinterpret_cast<int*>(take((size_t)h->ws_chunk * 4));
     __half* feat0 = reinterpret_cast<__half*>(take(rows_cap * 64 * 2));
     __half* fm[2] = {reinterpret_cast<__half*>(take(rows_cap * 128 * 2)), reinterpret_cast<__half*>(take(rows_cap * 128 * 2))};
     float* out32 = reinterpret_cast<float*>(take(rows_cap * 128 * 4));
@@ -390,9 +416,9 @@ extern "C" int rap_spinnet_extract(rap_spinnet_t* h, const float* points, int n_
     for (int k0 = 0; k0 < n_keypoints; k0 += chunk) {
         const int kc = n_keypoints - k0 < chunk ? n_keypoints - k0 : chunk;
         const int M = kc * KROWS;
-        patch_kernel<<<ceil_div(kc, 8), 256, 0, st>>>(pts_s, keypoints + (size_t)k0 * 3, n_points, kc, des_r, patches);
+        patch_kernel<<<ceil_div(kc, 8), 256, 0, st>>>(pts_s, keypoints + (size_t)k0 * 3, n_points, kc, des_r, patches, n_real);
         RAP_CUDA(cudaGetLastError());
-        voxel_feature_kernel<<<kc, 448, 0, st>>>(patches, kc, feat0);
+        voxel_feature_kernel<<<kc, 448, 0, st>>>(patches, n_real, kc, feat0);
         RAP_CUDA(cudaGetLastError());
         note_launch(2);
         const __half* in = feat0;
@@ -425,7 +451,7 @@ extern "C" int rap_test_spinnet_patches(const float* points, int n_points, const
     float* tmp = nullptr;
     RAP_CUDA(cudaMalloc(&tmp, (size_t)n_points * 12));
     gather_points_kernel<<<ceil_div(n_points, 256), 256, 0, st>>>(points, perm, tmp, n_points);
-    patch_kernel<<<ceil_div(n_keypoints, 8), 256, 0, st>>>(tmp, keypoints, n_points, n_keypoints, des_r, patches_out);
+    patch_kernel<<<ceil_div(n_keypoints, 8), 256, 0, st>>>(tmp, keypoints, n_points, n_keypoints, des_r, patches_out, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(RAP_ECUDA, "rap_test_spinnet_patches: %s", cudaGetErrorString(e));
