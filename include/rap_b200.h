@@ -124,6 +124,12 @@ int rap_fps_batched(const float* points, int n_clouds, int max_points, const int
                     int max_k, int64_t* indices_out, float* sampled_out, void* stream);
 int rap_statistical_outliers(const float* points, int n, int nb_neighbors, double std_ratio, uint8_t* keep_out, int* n_keep_out, void* stream);
 
+/* Evaluation metrics with ground truth: squared distance of every query point to its nearest target point of the same
+ * segment (cu_seqlens: device, n_segments + 1 entries shared by both packed clouds), optionally only over targets with a DIFFERENT label.
+ * Building block of compute_cd (reference eval/metrics.py:14-48) and compute_overlap_ratio (:625-691).  All pointers device. */
+int rap_segment_nn(const float* query, const float* target, const int32_t* cu_seqlens, int n_segments, const int32_t* label_query,
+                   const int32_t* label_target, float* min_dist2_out, void* stream);
+
 /* Pose application (demo.py:1330-1340, open3d PointCloud.transform): out = R p + t over a full-resolution cloud,
  * fp32 or fp64 points (device), the affine 4x4 row-major in HOST memory.  In-place (out == points) is allowed. */
 int rap_apply_transform(const void* points, long long n, int is_f64, const double* transform_4x4_host, void* out, void* stream);

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "rap_fps_capacity": (C.c_int, []),
     "rap_fps_batched": (C.c_int, [_f32p, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _f32p, _vp]),
     "rap_statistical_outliers": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_double, _vp, C.POINTER(C.c_int), _vp]),
+    "rap_segment_nn": (C.c_int, [_f32p, _f32p, _vp, C.c_int, _vp, _vp, _f32p, _vp]),
     "rap_apply_transform": (C.c_int, [_vp, C.c_longlong, C.c_int, C.POINTER(C.c_double), _vp, _vp]),
     "rap_bench_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int, C.POINTER(C.c_float)]),
     "rap_fmha_schedule": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

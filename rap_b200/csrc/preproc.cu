@@ -316,6 +316,29 @@ __global__ void threshold_kernel(const double* __restrict__ avg, int n, double t
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
 }
 
+// ------------------------------------------------------------------------------------------------ evaluation: nearest neighbours
+// out[i] = min over targets j of the SAME segment (cu_seqlens) with label_t[j] != label_q[i] (when labels are given) of |q_i - t_j|^2,
+// +inf if there is none.  Thread = query; the targets are read straight from L1/L2 (every lane of a warp reads the same address).
+// Serves the chamfer distance (eval/metrics.py:14-48, no labels, both directions) and the overlap ratio (:625-691, labels = part ids).
+__global__ void __launch_bounds__(256)
+segment_nn_kernel(const float* __restrict__ q, const float* __restrict__ t, const int* __restrict__ cu, int n_seg, const int* __restrict__ label_q,
+                  const int* __restrict__ label_t, int n_total, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    int lo = 0, hi = n_seg;                                  // segment of query i: cu[lo] <= i < cu[lo + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cu[mid] <= i) lo = mid; else hi = mid; }
+    const int s = cu[lo], e = cu[lo + 1];
+    const float x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+    const int lab = label_q ? label_q[i] : -1;
+    float best = INFINITY;
+    for (int j = s; j < e; ++j) {
+        const float dx = x - t[3 * j], dy = y - t[3 * j + 1], dz = z - t[3 * j + 2];
+        const float d = dx * dx + dy * dy + dz * dz;
+        if ((!label_t || label_t[j] != lab) && d < best) best = d;
+    }
+    out[i] = best;
+}
+
 // ------------------------------------------------------------------------------------------------ pose application
 // out = R p + t for every point of a full-resolution cloud (demo.py:1338-1340, open3d PointCloud.transform): 24 B/point of traffic.
 struct Rigid { double r[9], t[3]; };
@@ -332,6 +355,21 @@ __global__ void apply_transform_kernel(const T* __restrict__ in, T* __restrict__
 }  // namespace
 
 // ================================================================================================ C ABI
+extern "C" int rap_segment_nn(const float* query, const float* target, const int32_t* cu_seqlens, int n_segments, const int32_t* label_query,
+                              const int32_t* label_target, float* min_dist2_out, void* stream) {
+    RAP_REQUIRE(query && target && cu_seqlens && min_dist2_out && n_segments >= 1, "rap_segment_nn: bad argument");
+    RAP_REQUIRE((label_query == nullptr) == (label_target == nullptr), "rap_segment_nn: give both label arrays or neither");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int n_total = 0;
+    RAP_CUDA(cudaMemcpyAsync(&n_total, cu_seqlens + n_segments, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RAP_CUDA(cudaStreamSynchronize(st));
+    if (n_total <= 0) return RAP_OK;
+    segment_nn_kernel<<<ceil_div(n_total, 256), 256, 0, st>>>(query, target, cu_seqlens, n_segments, label_query, label_target, n_total, min_dist2_out);
+    RAP_CUDA(cudaGetLastError());
+    note_launch();
+    return RAP_OK;
+}
+
 extern "C" int rap_apply_transform(const void* points, long long n, int is_f64, const double* transform_4x4_host, void* out, void* stream) {
     RAP_REQUIRE(points && out && transform_4x4_host && n >= 0, "rap_apply_transform: bad argument");
     const double* T = transform_4x4_host;

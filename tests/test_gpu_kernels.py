@@ -265,3 +265,33 @@ def test_apply_transform_full_resolution(rap):
     with pytest.raises(RuntimeError):
         bad = T.copy(); bad[3, 0] = 0.1
         apply_transform(pts[:10], bad)
+
+
+def test_chamfer_and_overlap_match_reference_golden(rap, golden_dir):
+    """compute_cd / compute_overlap_ratio on the nearest-neighbour kernel vs the reference run verbatim (oracle/make_golden.py eval)."""
+    import os
+    from oracle.make_golden import eval_case, eval_gt_case
+    from rap_b200.rectified_point_flow.eval import compute_cd, compute_overlap_ratio
+    g = np.load(os.path.join(golden_dir, "eval.npz"))
+    d = eval_case()
+    gt = eval_gt_case(d)
+    pred, cu = d["pred"].cuda(), gt["cu2"].cuda()
+    cd = compute_cd(gt["gt"].cuda(), pred, cu)
+    _sync_check(rap)
+    np.testing.assert_allclose(cd.cpu().numpy(), g["cd"], rtol=1e-5)
+    ov = compute_overlap_ratio(pred, gt["ppp2"].cuda(), cu, taus=[0.05, 0.15, 0.4]).cpu().numpy()
+    n = np.diff(gt["cu2"].numpy())
+    assert ov.shape == (3, 2) and (np.abs(ov - g["overlap"]) <= 1.5 / n[None, :]).all()      # one borderline point may flip (cdist vs direct form)
+    # brute-force check at a size the golden does not cover, ragged segments, single-part object -> 0
+    gen = torch.Generator("cuda").manual_seed(2)
+    ppp = torch.tensor([[700, 324, 0], [500, 0, 0], [33, 64, 100]], device="cuda")
+    cu3 = torch.tensor([0, 1024, 1524, 1721], device="cuda")
+    pts = torch.rand(1721, 3, device="cuda", generator=gen)
+    got = compute_overlap_ratio(pts, ppp, cu3, taus=0.06)[0].cpu().numpy()
+    lab = torch.repeat_interleave(torch.arange(3, device="cuda").repeat(3), ppp.reshape(-1))
+    want = []
+    for a, b in zip(cu3[:-1].tolist(), cu3[1:].tolist()):
+        dm = torch.cdist(pts[a:b].double(), pts[a:b].double())
+        dm[lab[a:b, None] == lab[None, a:b]] = float("inf")
+        want.append(float((dm.min(1).values <= 0.06).double().mean()) if len(set(lab[a:b].tolist())) > 1 else 0.0)
+    assert np.abs(got - np.array(want)).max() < 3e-3 and got[1] == 0.0

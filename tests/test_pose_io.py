@@ -45,3 +45,20 @@ def test_relative_to_reference_and_suffixes(tmp_path):
     np.testing.assert_allclose(rel[0], np.eye(4), atol=1e-12)
     np.testing.assert_allclose(Ts[0] @ rel[2], Ts[2], atol=1e-12)
     assert relative_to_reference([]) == [] and save_transformation_files({}, 0, tmp_path, "x", 0) == []
+
+
+def test_pose_errors_match_reference():
+    """compute_transform_errors / _direct (reference eval/metrics.py:165-384, run verbatim for the golden) -- batched torch, runs anywhere."""
+    from oracle.make_golden import eval_gt_case
+    from rap_b200.rectified_point_flow.eval import compute_transform_errors, compute_transform_errors_direct
+    d = eval_case()
+    g = eval_gt_case(d)
+    re_, te_ = compute_transform_errors(d["cond"], g["gt"], g["R_gt2"], g["t_gt2"], g["R_pr2"], g["t_pr2"], g["ppp2"], g["anchor2"],
+                                        scale=g["scales2"], cu_seqlens_batch=g["cu2"])
+    np.testing.assert_allclose(re_.numpy(), G["rot_err"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(te_.numpy(), G["trans_err"], rtol=1e-5, atol=1e-5)
+    re_d, te_d = compute_transform_errors_direct(g["R_gt2"], g["t_gt2"], g["R_pr2"], g["t_pr2"], g["ppp2"], scale=g["scales2"])
+    np.testing.assert_allclose(re_d.numpy(), G["rot_err_direct"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(te_d.numpy(), G["trans_err_direct"], rtol=1e-5, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        compute_transform_errors(d["cond"], g["gt"], g["R_gt2"], g["t_gt2"], g["R_pr2"], g["t_pr2"], g["ppp2"], g["anchor2"], use_icp=True)
