@@ -485,6 +485,15 @@ extern "C" int rap_fps_batched(const float* points, int n_clouds, int max_points
         return launch_fps<8, true>(points, n_clouds, max_points, lengths, k, start_idx, max_k, C, out, sampled_out, st);
     }
     if (max_points <= 8 * kFpsThreads * 20) return launch_fps<20, true>(points, n_clouds, max_points, lengths, k, start_idx, max_k, 8, out, sampled_out, st);
+    // > 81920 points: 16-CTA clusters (opt-in size) keep the coordinates in registers; if this device cannot co-schedule 16 CTAs of this
+    // footprint the launch fails cleanly and the shared-memory variant (36 points per thread, 8 CTAs) takes over.
+    static int wide16 = -1;                               // RAP_FPS_CLUSTER16=0 disables (A/B measurements)
+    if (wide16 < 0) { const char* e = getenv("RAP_FPS_CLUSTER16"); wide16 = (e && atoi(e) == 0) ? 0 : 1; }
+    if (wide16 && max_points <= 16 * kFpsThreads * 20) {
+        if (launch_fps<20, true>(points, n_clouds, max_points, lengths, k, start_idx, max_k, 16, out, sampled_out, st) == RAP_OK) return RAP_OK;
+        cudaGetLastError();
+        wide16 = 0;
+    }
     return launch_fps<36, false>(points, n_clouds, max_points, lengths, k, start_idx, max_k, max_points <= 8 * kFpsThreads * 36 ? 8 : 16, out,
                                  sampled_out, st);
 }
