@@ -3,11 +3,15 @@
 // reference at flow_model/layer.py:106-111 (part-wise: segments = views) and :123-128 (global:
 // segments = scenes).  The two calls differ only in the segment table, so this is one kernel.
 //
-// One CTA = one 256-row query block (two 128-row tiles) of one head, one CTA per SM (193 KB smem, 512 TMEM columns).
-//   warp 0   : TMA producer  (Q tiles once; K and V blocks through separate 3-deep rings)
-//   warp 1   : UMMA issuer   (S_t = Q_t K^T into TMEM cols [128t,128t+128); O_t += P_t V into cols [256+64t, ...))
-//   warps 2-5: softmax of tile 0, warps 6-9: softmax of tile 1 (thread = query row: tcgen05.ld S, online max/sum in the
-//              log2 domain, P -> smem as fp16 in the K-major SWIZZLE_128B layout UMMA reads, lazy O rescale in TMEM)
+// One CTA = one work item: a 256-row query block (two 128-row tiles) of one head against a key range of its segment (the whole
+// segment, or a piece of it when the unit belongs to the last, partially filled wave -- fmha.cuh), one CTA per SM (161 KB smem, 512 TMEM
+// columns).
+//   warp 0   : TMA producer  (Q tiles once; K and V blocks through separate 4-deep rings)
+//   warp 1   : UMMA issuer   (per tile t: S_t = Q_t K^T -> TMEM cols [256t, +128);  O_t += P_t V -> cols [256t+192, +64), P_t read
+//              straight from TMEM cols [256t+128, +64) as the A operand (TS mode), V as an MN-major shared-memory B operand)
+//   warps 2-5: softmax of tile 0, warps 6-9: softmax of tile 1 (thread = query row: tcgen05.ld of the 128 scores, exponentials in the
+//              log2 domain against a stale reference exponent on packed f32x2 math, P written back to TMEM as fp16 pairs with tcgen05.st;
+//              O is only rescaled on the rare overflow path)
 #include <cstdlib>
 
 #include "fmha.cuh"
