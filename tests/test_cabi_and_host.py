@@ -180,3 +180,22 @@ def test_fmha_schedule_covers_every_key_block_once(cu):
         # the cost model (piece overhead ~4.5 key blocks) keeps the 32-block per-view launch whole and cuts the 64-block per-scene one
         plain, n_plain, _ = _fmha_schedule(cu, force=0)
         assert (n_plain == 0 and len(plain) == 256) if cu == [0, 4096, 8192] else (n_plain == 108 and len(plain) == 364)
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected before any CUDA call (errno-style code + rap_last_error text), so this runs on the CPU box."""
+    import ctypes as C
+    from rap_b200 import _lib
+    L = _lib.lib
+    n = C.c_int(0)
+    assert L.rap_voxel_downsample(None, 0, 0.5, None, C.byref(n), None) == -22 and b"rap_voxel_downsample" in L.rap_last_error()
+    assert L.rap_voxel_coverage(None, -1, 0, 1.0, C.byref(n), None) == -22
+    assert L.rap_voxel_coverage(None, 0, 0, 1.0, C.byref(n), None) == 0 and n.value == 0          # empty part: 0 voxels, no device work
+    assert L.rap_fps_batched(None, 1, 10, None, None, None, 5, None, None, None) == -22
+    assert L.rap_fps_capacity() >= 100_000                                                       # the reference's pre-FPS cap (20 x 5000)
+    assert L.rap_statistical_outliers(None, 5, 20, 2.0, None, C.byref(n), None) == -22
+    assert L.rap_segment_nn(None, None, None, 1, None, None, None, None) == -22
+    T = (C.c_double * 16)(*([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0.5, 0, 0, 1]))                 # not affine
+    assert L.rap_apply_transform(1, 10, 0, T, 1, None) == -22 and b"affine" in L.rap_last_error()
+    assert L.rap_procrustes_fit_sse(None, None, None, None, 1, None, None, None, None) == -22
+    assert L.rap_fmha_schedule(None, 1, 8, 0, None, 0, None, None) == -22
