@@ -38,9 +38,41 @@ def install(package: str = "rectified_point_flow") -> None:
     sys.modules.setdefault(f"{package}.utils.point_clouds", pc)
 
 
-def install_extractor(module: str = "dataset_process.extract_sample_features") -> None:
-    """Replace the reference's `FeatureExtractor` class (MiniSpinNet wrapper) by the CUDA extractor, leaving the rest of the
-    module (SampleProcessor, FPS, outlier removal, CLI) untouched.  No-op-safe: raises ImportError if the reference module is absent."""
+def install_extractor(module: str = "dataset_process.extract_sample_features", keypoint_selection: bool = True) -> None:
+    """Replace the reference's `FeatureExtractor` class (MiniSpinNet wrapper) by the CUDA extractor and -- with keypoint_selection --
+    `SampleProcessor` plus the helpers it and demo.py call (`voxel_down_sample_torch`, `calculate_voxel_coverage`, `apply_batched_fps`, ...)
+    by the GPU keypoint selection.  Raises ImportError if the reference module is absent."""
     ref = importlib.import_module(module)
     mine = importlib.import_module("rap_b200.dataset_process.extract_sample_features")
     ref.FeatureExtractor = mine.FeatureExtractor
+    if not keypoint_selection:
+        return
+    ref.SampleProcessor = mine.SampleProcessor
+    root = module.rsplit(".", 1)[0]                      # 'dataset_process'
+    for sub, names in (("utils.dataset_utils", ("voxel_down_sample_torch", "downsample_points")),
+                       ("utils.point_sampling_utils", ("calculate_voxel_coverage", "calculate_adaptive_sample_count_per_part",
+                                                       "allocate_fps_points", "apply_batched_fps"))):
+        src = importlib.import_module(f"rap_b200.dataset_process.{sub}")
+        for cand in (f"{root}.{sub}", sub):              # the reference imports these both as package members and as top-level `utils.*`
+            try:
+                dst = importlib.import_module(cand)
+            except Exception:
+                continue
+            for n in names:
+                setattr(dst, n, getattr(src, n))
+    for n in ("calculate_adaptive_sample_count_per_part", "allocate_fps_points", "apply_batched_fps"):
+        if hasattr(ref, n):                              # names bound by `from utils.point_sampling_utils import ...` (reference :53)
+            setattr(ref, n, getattr(importlib.import_module("rap_b200.dataset_process.utils.point_sampling_utils"), n))
+
+
+def install_eval(package: str = "rectified_point_flow") -> None:
+    """Replace the metric functions of `<package>.eval.metrics` that have CUDA mirrors (rigidity RMSE, chamfer, overlap ratio, pose
+    errors); the Evaluator class itself stays the reference's."""
+    ref = importlib.import_module(f"{package}.eval.metrics")
+    mine = importlib.import_module("rap_b200.rectified_point_flow.eval.metrics")
+    names = ("compute_rigidity_rmse", "compute_cd", "compute_overlap_ratio", "compute_transform_errors", "compute_transform_errors_direct")
+    targets = [ref] + [sys.modules[m] for m in (f"{package}.eval.evaluator", f"{package}.modeling") if m in sys.modules]
+    for mod in targets:                                  # evaluator.py / modeling.py bind the names with `from .metrics import ...`
+        for n in names:
+            if mod is ref or hasattr(mod, n):
+                setattr(mod, n, getattr(mine, n))

@@ -199,3 +199,21 @@ def test_argument_validation_needs_no_gpu():
     assert L.rap_apply_transform(1, 10, 0, T, 1, None) == -22 and b"affine" in L.rap_last_error()
     assert L.rap_procrustes_fit_sse(None, None, None, None, 1, None, None, None, None) == -22
     assert L.rap_fmha_schedule(None, 1, 8, 0, None, 0, None, None) == -22
+
+
+def test_install_eval_patches_reference_modules():
+    """rap_b200.install_eval() swaps the metric functions inside the reference's own eval modules (needs /root/reference: build container)."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference sources not present")
+    import rap_b200
+    ns = ref_loader.load_reference_eval()
+    try:
+        rap_b200.install_eval()
+        from rap_b200.rectified_point_flow.eval import metrics as mine
+        for n in ("compute_rigidity_rmse", "compute_cd", "compute_overlap_ratio", "compute_transform_errors", "compute_transform_errors_direct"):
+            assert getattr(ns.metrics, n) is getattr(mine, n)
+            assert not hasattr(ns.evaluator, n) or getattr(ns.evaluator, n) is getattr(mine, n)      # names evaluator.py imported by value
+        assert ns.metrics.compute_ecdf.__module__.endswith("eval.metrics") and "rap_b200" not in ns.metrics.compute_ecdf.__module__
+    finally:
+        ref_loader.unload_reference()
