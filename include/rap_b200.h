@@ -67,20 +67,23 @@ int rap_sample_euler(rap_plan_t* plan, const float* x_1, int num_steps, int rigi
 /* ---- Procrustes: replaces procrustes.py:40-118 --------------------------------------------------
  * cu_seqlens_part: device int32 [n_parts+1] over the packed (T,3) clouds; slot: device int32 [n_parts]
  * giving b*max_parts+p of each non-empty part (NULL = identity).  rotations (slots,3,3) / translations
- * (slots,3) must be zero-initialised by the caller so empty slots read as zeros (procrustes.py:71-76). */
+ * (slots,3) must be zero-initialised by the caller so empty slots read as zeros (procrustes.py:71-76).
+ * n_points = rows of the packed clouds: the reference asserts sum(points_per_part) == N on the host (utils/point_clouds.py:41-44); here
+ * a part reaching past n_points is skipped on the device (nothing read or written out of bounds) and flagged in the error word that
+ * rap_device_error() returns (code 0xB1).  n_points <= 0 disables the check. */
 int rap_procrustes_fit(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot,
-                       int n_parts, float* rotations, float* translations, void* stream);
+                       int n_parts, int64_t n_points, float* rotations, float* translations, void* stream);
 /* out = (R cond + t) * w_rigid + mix * w_mix per part, (R,t) fitted cond -> prediction; mix may be NULL.
  * rigidify_prediction_with_procrustes is w_rigid=1, mix=NULL; sampler.py:60 is w_rigid=1-t+dt, w_mix=t-dt. */
-int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_seqlens_part, int n_parts,
+int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_seqlens_part, int n_parts, int64_t n_points,
                             float* out, const float* mix, float w_rigid, float w_mix, void* stream);
 /* Generation selection (modeling.py:456-547, eval/metrics.py:511-622): per slot sum of squared residuals |R src + t - tgt|^2, either
  * fused with the fit (one launch per trajectory step instead of fit_transformations + compute_rigidity_rmse host loops) or for a
  * given (R,t).  sse (slots) must be zero-initialised by the caller. */
 int rap_procrustes_fit_sse(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot, int n_parts,
-                           float* rotations, float* translations, float* sse, void* stream);
+                           int64_t n_points, float* rotations, float* translations, float* sse, void* stream);
 int rap_rigid_sse(const float* source, const float* target, const int32_t* cu_seqlens_part, const int32_t* slot, int n_parts,
-                  const float* rotations, const float* translations, float* sse, void* stream);
+                  int64_t n_points, const float* rotations, const float* translations, float* sse, void* stream);
 /* Plan-bound convenience wrappers using the plan's own part table. */
 int rap_plan_fit(rap_plan_t* plan, const float* source, const float* target, float* rotations, float* translations, void* stream);
 int rap_plan_rigidify(rap_plan_t* plan, const float* prediction, const float* condition, float* out, void* stream);

@@ -25,6 +25,16 @@ CASES = {
     "ragged_b2_v3_L2_s3_rigid": (2, 2, 3, [200, 136, 72], 3, True),
 }
 
+# Cases at the sizes BASELINE.json / bench.py quote (VERDICT r01 "pin parity at the configs you quote").  The reference needs minutes per
+# case on the build container's host cores, and full trajectories would be megabytes, so these store a compact subset:
+# name: (num_layers, scenes, views, pts_per_view, steps, rigidity, max_parts, trajectory steps kept)
+BIG_CASES = {
+    "cfg2_2x4096_s20": (12, 1, 2, 4096, 20, False, 2, (0, 9, 19)),              # configs[1]: the headline workload, all 20 flow steps
+    "cfg3_4x4096_s3_rigid": (12, 1, 4, 4096, 3, True, 4, (0, 2)),                # configs[2] shape, rigidity forcing on (RAP_inference.yaml:58)
+    "cfg1_2x512_s5_p512": (12, 1, 2, 512, 5, True, 512, (0, 4)),                 # max_parts: 512 padding (RAP_inference.yaml:33)
+    "small_L2_s70": (2, 2, 2, [96, 64], 70, False, 3, (0, 63, 64, 69)),          # more than 64 flow steps (timestep table beyond one block)
+}
+
 
 def input_checksum(batch, sd) -> float:
     s = float(batch.cond.double().sum() + batch.features.double().sum() + batch.x_1.double().sum())
@@ -40,12 +50,20 @@ def build_reference_model(ref, cfg: DiTConfig, sd):
     return m.eval()
 
 
+def case_params(name):
+    """(L, B, V, N, S, rigid, max_parts, kept trajectory steps or None = all) for a CASES / BIG_CASES entry."""
+    if name in CASES:
+        L, B, V, N, S, rigid = CASES[name]
+        return L, B, V, N, S, rigid, V + 2, None     # two padded empty part slots, like max_parts padding
+    return BIG_CASES[name]
+
+
 @torch.inference_mode()
 def run_case(ref, name):
-    L, B, V, N, S, rigid = CASES[name]
+    L, B, V, N, S, rigid, P, keep = case_params(name)
     cfg = DiTConfig(num_layers=L)
     sd = make_state_dict(cfg, seed=0)
-    batch = make_batch(B, V, N, max_parts=V + 2)     # two padded empty part slots, like max_parts padding
+    batch = make_batch(B, V, N, max_parts=P)
     model = build_reference_model(ref, cfg, sd)
     calls = []
 
@@ -72,9 +90,12 @@ def run_case(ref, name):
     rigid_once = ref.procrustes.rigidify_prediction_with_procrustes(pred, batch.cond, batch.points_per_part,
                                                                     batch.cu_seqlens_batch)
     dt = time.perf_counter() - t0
+    ep, tr = res["end_point_trajectory"], res["trajectory"]
+    if keep is not None:
+        ep, tr = ep[list(keep)], tr[list(keep)]
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
-        end_point_trajectory=res["end_point_trajectory"].numpy(), trajectory=res["trajectory"].numpy(),
+        end_point_trajectory=ep.numpy(), trajectory=tr.numpy(), kept_steps=np.array(keep if keep is not None else range(S)),
         rotations=R.numpy(), translations=t.numpy(), fwd_timesteps=ts.numpy(), fwd_velocity=fwd["velocity"].numpy(),
         fwd_features_checksum=np.float64(fwd["transformer_features"].double().abs().sum()),
         fwd_features_head=fwd["transformer_features"][:8].numpy(), rigidified=rigid_once.numpy(),
@@ -273,8 +294,9 @@ def main():
     if sys.argv[1:] == ["eval"]:
         eval_goldens()
         return
-    procrustes_kats(ref)
-    for name in (sys.argv[1:] or CASES):
+    if not sys.argv[1:]:
+        procrustes_kats(ref)
+    for name in (sys.argv[1:] or list(CASES) + list(BIG_CASES)):
         run_case(ref, name)
     if not sys.argv[1:]:
         spinnet_goldens()

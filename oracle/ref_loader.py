@@ -199,10 +199,69 @@ def load_reference_eval():
     return ns
 
 
+def load_reference_modeling(install_rap_b200: bool = True):
+    """The reference's own `modeling.py` (class `RectifiedPointFlow`: `_prepare_data`, `sample_rectified_flow`, `test_step`) executed
+    verbatim, with -- when `install_rap_b200` -- `rectified_point_flow.{sampler,procrustes,flow_model}` aliased to the rap_b200 mirrors
+    BEFORE modeling.py runs its `from .sampler import get_sampler` / `from .procrustes import fit_transformations`, i.e. exactly what
+    `rap_b200.install()` does for sample.py / demo.py.  `lightning` is absent offline: `LightningModule` becomes a plain `nn.Module`
+    with the `device` property and no-op loggers (the only Lightning features these code paths touch)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    unload_reference()
+    _install_shims()
+    root = os.path.join(REFERENCE_ROOT, _PKG)
+    for name, path in ((_PKG, root), (_PKG + ".utils", os.path.join(root, "utils")), (_PKG + ".eval", os.path.join(root, "eval"))):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        m._rap_bypass = True
+        sys.modules[name] = m
+    importlib.import_module(_PKG + ".utils.point_clouds")          # the reference's own glue (install() only fills it in if absent)
+    if install_rap_b200:
+        import rap_b200
+        rap_b200.install(_PKG)
+    else:
+        for sub in ("procrustes", "sampler", "flow_model"):
+            importlib.import_module(f"{_PKG}.{sub}")
+
+    class LightningModule(nn.Module):
+        @property
+        def device(self):
+            p = next(self.parameters(), None)
+            return p.device if p is not None else torch.device("cpu")
+
+        def log(self, *a, **k):
+            pass
+
+        def log_dict(self, *a, **k):
+            pass
+
+    L = types.ModuleType("lightning")
+    L.__path__ = []
+    L.LightningModule = LightningModule
+    sys.modules["lightning"] = L
+    for name, attrs in (("open3d", {}), ("pytorch3d", {}), ("pytorch3d.loss", {}), ("pytorch3d.loss.chamfer", {"chamfer_distance": None}),
+                        ("pytorch3d.ops", {"iterative_closest_point": None}), (_PKG + ".utils.render", {"part_ids_to_colors": None})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            if not hasattr(sys.modules[name], k):
+                setattr(sys.modules[name], k, v)
+    ns = types.SimpleNamespace()
+    ns.modeling = importlib.import_module(_PKG + ".modeling")
+    ns.sampler = sys.modules[_PKG + ".sampler"]
+    ns.procrustes = sys.modules[_PKG + ".procrustes"]
+    ns.flow_model = sys.modules[_PKG + ".flow_model"]
+    return ns
+
+
 def unload_reference() -> None:
     """Remove the bypass packages so `rap_b200.install()` can be tested after."""
     for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:
         del sys.modules[k]
+    if getattr(sys.modules.get("lightning"), "__path__", None) == []:      # our stand-in, not a real install
+        del sys.modules["lightning"]
 
 
 # ----------------------------------------------------------------------------

@@ -43,10 +43,10 @@ PROTOTYPES = {
     "rap_plan_set_condition": (C.c_int, [_vp, _f32p, _f32p, _f32p, _u8p, _vp]),
     "rap_dit_forward": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _vp]),
     "rap_sample_euler": (C.c_int, [_vp, _f32p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _vp]),
-    "rap_procrustes_fit": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, _f32p, _f32p, _vp]),
-    "rap_procrustes_rigidify": (C.c_int, [_f32p, _f32p, _vp, C.c_int, _f32p, _f32p, C.c_float, C.c_float, _vp]),
-    "rap_procrustes_fit_sse": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, _f32p, _f32p, _f32p, _vp]),
-    "rap_rigid_sse": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, _f32p, _f32p, _f32p, _vp]),
+    "rap_procrustes_fit": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, C.c_int64, _f32p, _f32p, _vp]),
+    "rap_procrustes_rigidify": (C.c_int, [_f32p, _f32p, _vp, C.c_int, C.c_int64, _f32p, _f32p, C.c_float, C.c_float, _vp]),
+    "rap_procrustes_fit_sse": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, C.c_int64, _f32p, _f32p, _f32p, _vp]),
+    "rap_rigid_sse": (C.c_int, [_f32p, _f32p, _vp, _vp, C.c_int, C.c_int64, _f32p, _f32p, _f32p, _vp]),
     "rap_plan_fit": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _vp]),
     "rap_plan_rigidify": (C.c_int, [_vp, _f32p, _f32p, _f32p, _vp]),
     "rap_spinnet_create": (C.c_int, [C.POINTER(_vp)]),

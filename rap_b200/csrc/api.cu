@@ -65,11 +65,12 @@ bool pdl_enabled() {
     return v == 1;
 }
 
-int num_sms() {
-    static int n = 0;
+int num_sms() {                                             // per device: a process may drive different devices
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = cache[dev & 63];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
@@ -485,27 +486,42 @@ namespace {
 // kept in L2 by an access-policy window on the launching stream: the per-layer working set (qkv, attention output, GEGLU mid) is larger
 // than L2, so without it every epilogue write of h turns into an HBM write-back and every re-read into an HBM read.
 // RAP_L2_PERSIST=0 disables (A/B measurements).  Failures are ignored: it is a hint.
-void pin_residual_stream(rap_plan* pl, cudaStream_t st) {
-    static int enabled = -1;
-    static size_t carve = 0, max_window = 0;
-    if (enabled < 0) {
+struct L2Policy { int enabled = -1; size_t carve = 0, max_window = 0; };
+L2Policy& l2_policy() {                                   // per device: limits and the carve-out differ between devices of one process
+    static L2Policy pol[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    L2Policy& p = pol[dev & 63];
+    if (p.enabled < 0) {
         const char* e = getenv("RAP_L2_PERSIST");
-        enabled = (e && atoi(e) == 0) ? 0 : 1;
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess) carve = (size_t)v;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) max_window = (size_t)v;
-        if (!carve || !max_window || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(carve, (size_t)48 << 20)) != cudaSuccess) enabled = 0;
-        carve = std::min(carve, (size_t)48 << 20);
+        p.enabled = (e && atoi(e) == 0) ? 0 : 1;
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess) p.carve = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) p.max_window = (size_t)v;
+        p.carve = std::min(p.carve, (size_t)48 << 20);
+        if (!p.carve || !p.max_window || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, p.carve) != cudaSuccess) p.enabled = 0;
         cudaGetLastError();
     }
-    if (!enabled || !pl->resid_bytes) return;
+    return p;
+}
+void pin_residual_stream(rap_plan* pl, cudaStream_t st) {
+    const L2Policy& pol = l2_policy();
+    if (!pol.enabled || !pl->resid_bytes) return;
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = pl->h;
-    attr.accessPolicyWindow.num_bytes = std::min(pl->resid_bytes, max_window);
-    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.num_bytes = std::min(pl->resid_bytes, pol.max_window);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)pol.carve / (double)attr.accessPolicyWindow.num_bytes);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+// The window is a property of the CALLER's stream: take it off again when the call has enqueued its kernels (launches already enqueued
+// keep the policy they were launched with), so later work of the application on that stream is not steered into the carve-out.
+void unpin_residual_stream(cudaStream_t st) {
+    if (!l2_policy().enabled) return;
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.num_bytes = 0;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();
 }
@@ -578,6 +594,7 @@ extern "C" int rap_dit_forward(rap_plan_t* pl, const float* x, const float* time
     RAP_TRY(dit_body(pl, x, 0, true, st));
     RAP_TRY(launch_head_final(pl->y2, pl->dit->wh4, pl->T, velocity, nullptr, 0.f, 0.f, nullptr, nullptr, st));
     if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->h, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
+    unpin_residual_stream(st);
     return RAP_OK;
 }
 
@@ -589,7 +606,7 @@ extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t row = (size_t)pl->T * 3;
     pin_residual_stream(pl, st);
-    sampler_timesteps_kernel<<<1, 64, 0, st>>>(pl->tbuf, num_steps);
+    sampler_timesteps_kernel<<<ceil_div(num_steps, 64), 64, 0, st>>>(pl->tbuf, num_steps);
     RAP_CUDA(cudaGetLastError());
     note_launch(1);
     RAP_TRY(ada_table(pl, num_steps, st));
@@ -609,41 +626,42 @@ extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps,
     }
     if (x_final) RAP_CUDA(cudaMemcpyAsync(x_final, pl->x_t, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));
     if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->h, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
+    unpin_residual_stream(st);
     return RAP_OK;
 }
 
 // ======================================================================================= procrustes
 extern "C" int rap_procrustes_fit(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
-                                  float* rotations, float* translations, void* stream) {
+                                  int64_t n_points, float* rotations, float* translations, void* stream) {
     RAP_REQUIRE(source && target && cu_part && rotations && translations && n_parts >= 0, "rap_procrustes_fit: bad argument");
     return launch_procrustes(source, target, cu_part, slot, n_parts, rotations, translations, nullptr, nullptr, nullptr, 0.f, 0.f,
-                             static_cast<cudaStream_t>(stream));
+                             static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, n_points);
 }
-extern "C" int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_part, int n_parts, float* out,
-                                       const float* mix, float w_rigid, float w_mix, void* stream) {
+extern "C" int rap_procrustes_rigidify(const float* prediction, const float* condition, const int32_t* cu_part, int n_parts, int64_t n_points,
+                                       float* out, const float* mix, float w_rigid, float w_mix, void* stream) {
     RAP_REQUIRE(prediction && condition && cu_part && out && n_parts >= 0, "rap_procrustes_rigidify: bad argument");
     return launch_procrustes(condition, prediction, cu_part, nullptr, n_parts, nullptr, nullptr, out, nullptr, mix, w_rigid, w_mix,
-                             static_cast<cudaStream_t>(stream));
+                             static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, n_points);
 }
 extern "C" int rap_procrustes_fit_sse(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
-                                      float* rotations, float* translations, float* sse, void* stream) {
+                                      int64_t n_points, float* rotations, float* translations, float* sse, void* stream) {
     RAP_REQUIRE(source && target && cu_part && rotations && translations && sse && n_parts >= 0, "rap_procrustes_fit_sse: bad argument");
     return launch_procrustes(source, target, cu_part, slot, n_parts, rotations, translations, nullptr, nullptr, nullptr, 0.f, 0.f,
-                             static_cast<cudaStream_t>(stream), sse);
+                             static_cast<cudaStream_t>(stream), sse, nullptr, nullptr, n_points);
 }
 extern "C" int rap_rigid_sse(const float* source, const float* target, const int32_t* cu_part, const int32_t* slot, int n_parts,
-                             const float* rotations, const float* translations, float* sse, void* stream) {
+                             int64_t n_points, const float* rotations, const float* translations, float* sse, void* stream) {
     RAP_REQUIRE(source && target && cu_part && rotations && translations && sse && n_parts >= 0, "rap_rigid_sse: bad argument");
     return launch_procrustes(source, target, cu_part, slot, n_parts, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f,
-                             static_cast<cudaStream_t>(stream), sse, rotations, translations);
+                             static_cast<cudaStream_t>(stream), sse, rotations, translations, n_points);
 }
 extern "C" int rap_plan_fit(rap_plan_t* pl, const float* source, const float* target, float* rotations, float* translations, void* stream) {
     RAP_REQUIRE(pl, "rap_plan_fit: NULL plan");
-    return rap_procrustes_fit(source, target, pl->cu_part, pl->slot, pl->VP, rotations, translations, stream);
+    return rap_procrustes_fit(source, target, pl->cu_part, pl->slot, pl->VP, pl->T, rotations, translations, stream);
 }
 extern "C" int rap_plan_rigidify(rap_plan_t* pl, const float* prediction, const float* condition, float* out, void* stream) {
     RAP_REQUIRE(pl, "rap_plan_rigidify: NULL plan");
-    return rap_procrustes_rigidify(prediction, condition, pl->cu_part, pl->VP, out, nullptr, 1.0f, 0.0f, stream);
+    return rap_procrustes_rigidify(prediction, condition, pl->cu_part, pl->VP, pl->T, out, nullptr, 1.0f, 0.0f, stream);
 }
 
 // ======================================================================================= micro entry points

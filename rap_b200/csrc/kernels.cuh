@@ -45,9 +45,10 @@ int launch_pack(const float* src, void* dst, int dst_is_half, const PackSpec& sp
 int launch_procrustes(const float* src, const float* tgt, const int* cu_part, const int* slot, int n_parts,
                       float* R_out, float* t_out, float* apply_out, float* apply_out2, const float* mix,
                       float w_rigid, float w_mix, cudaStream_t st, float* sse_out = nullptr, const float* R_in = nullptr,
-                      const float* t_in = nullptr);
+                      const float* t_in = nullptr, long long n_points = 0);
 //   sse_out      : per slot sum of squared residuals |R src + t - tgt|^2 (rigidity RMSE for generation selection)
 //   R_in / t_in  : evaluate a GIVEN transform (slot-indexed) instead of fitting one
+//   n_points     : rows of src/tgt (> 0: parts reaching past it are skipped and flagged in the device error word)
 
 void kabsch_host(const double* H9, double* R9);
 

@@ -6,6 +6,7 @@
 // as the reference's fp32 torch.linalg.svd; the point data path is fp32.
 #include "../../include/rap_b200.h"
 #include "kernels.cuh"
+#include "sm100.cuh"
 
 namespace rap {
 namespace {
@@ -102,13 +103,20 @@ __global__ void __launch_bounds__(kThreads)
 procrustes_kernel(const float* __restrict__ src, const float* __restrict__ tgt, const int* __restrict__ cu_part,
                   const int* __restrict__ slot, float* __restrict__ R_out, float* __restrict__ t_out,
                   float* __restrict__ apply_out, float* __restrict__ apply_out2, const float* __restrict__ mix,
-                  float w_rigid, float w_mix, float* __restrict__ sse_out, const float* __restrict__ R_in, const float* __restrict__ t_in) {
+                  float w_rigid, float w_mix, float* __restrict__ sse_out, const float* __restrict__ R_in, const float* __restrict__ t_in,
+                  long long n_points) {
     __shared__ double red[(kThreads / 32) * 9];
     __shared__ double res[9];
     __shared__ float Rt[12];
     const int part = blockIdx.x;
     const int s = cu_part[part], e = cu_part[part + 1], n = e - s;
     if (n <= 0) return;
+    // The reference asserts sum(points_per_part) == N on the host (utils/point_clouds.py:41-44); here a part table that runs past the
+    // clouds is refused on the device (no read or write out of bounds) and reported through the error word (rap_device_error).
+    if (n_points > 0 && (s < 0 || e > n_points)) {
+        if (threadIdx.x == 0) atomicCAS(&g_dev_error, 0u, 0xB1u | ((unsigned)part << 8));
+        return;
+    }
     const float* S = src + (size_t)s * 3;
     const float* G = tgt + (size_t)s * 3;
     const int sl_io = slot ? slot[part] : part;
@@ -189,10 +197,10 @@ void kabsch_host(const double* H, double* R) { kabsch_from_covariance(H, R); }
 
 int launch_procrustes(const float* src, const float* tgt, const int* cu_part, const int* slot, int n_parts,
                       float* R_out, float* t_out, float* apply_out, float* apply_out2, const float* mix,
-                      float w_rigid, float w_mix, cudaStream_t st, float* sse_out, const float* R_in, const float* t_in) {
+                      float w_rigid, float w_mix, cudaStream_t st, float* sse_out, const float* R_in, const float* t_in, long long n_points) {
     if (n_parts <= 0) return RAP_OK;
     ProfScope _ps(KC_PROCRUSTES, st);
-    procrustes_kernel<<<n_parts, kThreads, 0, st>>>(src, tgt, cu_part, slot, R_out, t_out, apply_out, apply_out2, mix, w_rigid, w_mix, sse_out, R_in, t_in);
+    procrustes_kernel<<<n_parts, kThreads, 0, st>>>(src, tgt, cu_part, slot, R_out, t_out, apply_out, apply_out2, mix, w_rigid, w_mix, sse_out, R_in, t_in, n_points);
     RAP_CUDA(cudaGetLastError());
     note_launch();
     return RAP_OK;

@@ -20,7 +20,7 @@ def compute_rigidity_rmse(pointclouds_input: torch.Tensor, pointclouds_pred: tor
     R = rotations_pred.detach().to(s.device, torch.float32).contiguous()
     t = translations_pred.detach().to(s.device, torch.float32).contiguous()
     sse = torch.zeros(B, P, device=s.device)
-    check(lib.rap_rigid_sse(ptr(s), ptr(g), ptr(cu), None, B * P, ptr(R), ptr(t), ptr(sse), stream_ptr()), "rap_rigid_sse")
+    check(lib.rap_rigid_sse(ptr(s), ptr(g), ptr(cu), None, B * P, s.shape[0], ptr(R), ptr(t), ptr(sse), stream_ptr()), "rap_rigid_sse")
     n = points_per_part.to(s.device, torch.float32)
     valid = n > 0
     if average_per_part:
@@ -41,7 +41,7 @@ def fit_and_rigidity_sse(source: torch.Tensor, target: torch.Tensor, points_per_
     R = torch.zeros(B, P, 3, 3, device=s.device)
     t = torch.zeros(B, P, 3, device=s.device)
     sse = torch.zeros(B, P, device=s.device)
-    check(lib.rap_procrustes_fit_sse(ptr(s), ptr(g), ptr(cu), None, B * P, ptr(R), ptr(t), ptr(sse), stream_ptr()), "rap_procrustes_fit_sse")
+    check(lib.rap_procrustes_fit_sse(ptr(s), ptr(g), ptr(cu), None, B * P, s.shape[0], ptr(R), ptr(t), ptr(sse), stream_ptr()), "rap_procrustes_fit_sse")
     return R, t, sse
 
 
@@ -58,7 +58,7 @@ def trajectory_rigidity_rmse(condition: torch.Tensor, trajectory: torch.Tensor, 
     t = torch.zeros(B, P, 3, device=s.device)
     sse = torch.zeros(S, B, P, device=s.device)
     for i in range(S):
-        check(lib.rap_procrustes_fit_sse(ptr(s), ptr(traj[i]), ptr(cu), None, B * P, ptr(R), ptr(t), ptr(sse[i]), stream_ptr()),
+        check(lib.rap_procrustes_fit_sse(ptr(s), ptr(traj[i]), ptr(cu), None, B * P, s.shape[0], ptr(R), ptr(t), ptr(sse[i]), stream_ptr()),
               "rap_procrustes_fit_sse")
     n = points_per_part.to(s.device, torch.float32).sum(1)
     rmse = torch.sqrt(sse.sum(2) / n.clamp(min=1))                       # (S,B)

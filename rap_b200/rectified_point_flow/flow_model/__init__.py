@@ -93,7 +93,7 @@ class PointCloudDiT(nn.Module):
                                        _linear(embed_dim // 2, out_dim, bias=False))
         self._handle: DiTHandle | None = None
         self._handle_key = None
-        self._plans: list[tuple[tuple, tuple, Plan]] = []      # (key, strong refs, plan), most recent last
+        self._plans: list[dict] = []      # {content key, identity keys -> strong refs, plan}, most recently used last
 
     # ------------------------------------------------------------------ C handles
     def _weights_key(self):
@@ -115,19 +115,32 @@ class PointCloudDiT(nn.Module):
 
     def plan(self, cu_seqlens_batch: torch.Tensor, cu_seqlens_part: torch.Tensor, points_per_part: torch.Tensor | None = None,
              max_timesteps: int = 64) -> Plan:
-        """Cached per batch layout.  The cache holds strong references to the key tensors so a recycled device
-        address can never alias a stale layout; the one host sync per new layout replaces the reference's
-        per-step `.tolist()` / boolean-index syncs."""
-        key = (cu_seqlens_batch.data_ptr(), cu_seqlens_batch._version, cu_seqlens_part.data_ptr(), cu_seqlens_part._version)
+        """Cached per batch layout, two-level: (1) the identity of the two cu_seqlens tensors (`data_ptr`, `_version`) -- no host
+        sync, hit whenever the caller reuses its tensors (the fused sampler, bench loops); (2) the layout CONTENT -- the
+        reference's `_prepare_data` (modeling.py:217-224) builds fresh cu_seqlens tensors for every batch, so identical layouts
+        arrive under new addresses; one small D2H copy (the same sync the reference pays for its `.max().item()` / `.tolist()`
+        calls) finds the existing plan instead of re-creating several hundred MB of workspace.  The cache holds strong
+        references to the identity-key tensors so a recycled device address can never alias a stale layout."""
+        ident = (cu_seqlens_batch.data_ptr(), cu_seqlens_batch._version, cu_seqlens_part.data_ptr(), cu_seqlens_part._version)
         h = self.handle()
-        for k, _, p in self._plans:
-            if k == key and p.max_timesteps >= max_timesteps:
-                return p
+        for e in self._plans:
+            if ident in e["idents"] and e["plan"].max_timesteps >= max_timesteps:
+                return e["plan"]
         cu_b = cu_seqlens_batch.detach().cpu().numpy().astype(np.int64)
         cu_p = cu_seqlens_part.detach().cpu().numpy().astype(np.int64)
         ppp = points_per_part.detach().cpu().numpy() if points_per_part is not None else points_per_part_from_cu(cu_b, cu_p)
+        ppp = np.asarray(ppp, dtype=np.int64)
+        # Empty part slots do not change the layout (the plan only keeps non-empty parts and their slot index b*P+p), but P does.
+        content = (cu_b.tobytes(), cu_p.tobytes(), ppp.shape, ppp.tobytes())
+        for i, e in enumerate(self._plans):
+            if e["content"] == content and e["plan"].max_timesteps >= max_timesteps:
+                e["idents"][ident] = (cu_seqlens_batch, cu_seqlens_part)
+                while len(e["idents"]) > 8:
+                    e["idents"].pop(next(iter(e["idents"])))
+                self._plans.append(self._plans.pop(i))          # most recently used last
+                return e["plan"]
         p = Plan(h, cu_b, ppp, max_timesteps)
-        self._plans.append((key, (cu_seqlens_batch, cu_seqlens_part), p))
+        self._plans.append({"content": content, "idents": {ident: (cu_seqlens_batch, cu_seqlens_part)}, "plan": p})
         del self._plans[:-4]
         return p
 

@@ -17,9 +17,15 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).reshape(-1, 3).contiguous()
 
 
-def _slot_offsets(points_per_part: torch.Tensor, device) -> torch.Tensor:
+def _slot_offsets(points_per_part: torch.Tensor, device, n_points: int | None = None) -> torch.Tensor:
     """cu_seqlens over ALL (b,p) slots in packing order; empty slots become zero-length parts that the kernel
-    skips, so no host sync (`ppp[ppp>0]`) is needed and slot index == b*P+p."""
+    skips, so no host sync (`ppp[ppp>0]`) is needed and slot index == b*P+p.
+
+    The reference asserts `sum(points_per_part) == N` (utils/point_clouds.py:41-44).  A host-resident table is checked
+    here the same way; a device-resident one is not read back (that would be the host sync this path removes) -- the
+    kernel gets N instead, skips any part that reaches past it and flags it in the device error word."""
+    if n_points is not None and not points_per_part.is_cuda and int(points_per_part.sum()) != n_points:
+        raise ValueError(f"points_per_part sums to {int(points_per_part.sum())}, but the point cloud has {n_points} points")
     cu = torch.zeros(points_per_part.numel() + 1, dtype=torch.int32, device=device)
     cu[1:] = torch.cumsum(points_per_part.to(device).reshape(-1), 0)
     return cu
@@ -33,7 +39,7 @@ def solve_procrustes(source_pcd: torch.Tensor, target_pcd: torch.Tensor) -> tupl
     cu = torch.tensor([0, s.shape[0]], dtype=torch.int32, device=s.device)
     R = torch.zeros(1, 3, 3, device=s.device)
     t = torch.zeros(1, 3, device=s.device)
-    check(lib.rap_procrustes_fit(ptr(s), ptr(g), ptr(cu), None, 1, ptr(R), ptr(t), stream_ptr()), "rap_procrustes_fit")
+    check(lib.rap_procrustes_fit(ptr(s), ptr(g), ptr(cu), None, 1, s.shape[0], ptr(R), ptr(t), stream_ptr()), "rap_procrustes_fit")
     return R[0], t[0]
 
 
@@ -45,10 +51,10 @@ def fit_transformations(source_pcds: torch.Tensor, target_pcds: torch.Tensor, po
         raise ValueError("cu_seqlens_batch is required when pointclouds has shape (TP, 3)")
     s, g = _prep(source_pcds), _prep(target_pcds)
     B, P = points_per_part.shape
-    cu = _slot_offsets(points_per_part, s.device)
+    cu = _slot_offsets(points_per_part, s.device, s.shape[0])
     R = torch.zeros(B, P, 3, 3, device=s.device)
     t = torch.zeros(B, P, 3, device=s.device)
-    check(lib.rap_procrustes_fit(ptr(s), ptr(g), ptr(cu), None, B * P, ptr(R), ptr(t), stream_ptr()), "rap_procrustes_fit")
+    check(lib.rap_procrustes_fit(ptr(s), ptr(g), ptr(cu), None, B * P, s.shape[0], ptr(R), ptr(t), stream_ptr()), "rap_procrustes_fit")
     return R, t
 
 
@@ -60,9 +66,9 @@ def rigidify_prediction_with_procrustes(prediction: torch.Tensor, condition: tor
         raise ValueError("cu_seqlens_batch is required when pointclouds has shape (TP, 3)")
     p, c = _prep(prediction), _prep(condition)
     B, P = points_per_part.shape
-    cu = _slot_offsets(points_per_part, p.device)
+    cu = _slot_offsets(points_per_part, p.device, p.shape[0])
     out = torch.zeros_like(p)
-    check(lib.rap_procrustes_rigidify(ptr(p), ptr(c), ptr(cu), B * P, ptr(out), None, 1.0, 0.0, stream_ptr()), "rap_procrustes_rigidify")
+    check(lib.rap_procrustes_rigidify(ptr(p), ptr(c), ptr(cu), B * P, p.shape[0], ptr(out), None, 1.0, 0.0, stream_ptr()), "rap_procrustes_rigidify")
     return out.view(prediction.shape)
 
 
@@ -70,8 +76,8 @@ def rigidify_and_interpolate(prediction, condition, x_1, points_per_part, w_rigi
     """Fused sampler.py:59-60: rigid(prediction) * w_rigid + x_1 * w_noise in the same launch."""
     p, c, n = _prep(prediction), _prep(condition), _prep(x_1)
     B, P = points_per_part.shape
-    cu = _slot_offsets(points_per_part, p.device)
+    cu = _slot_offsets(points_per_part, p.device, p.shape[0])
     out = torch.empty_like(p)
-    check(lib.rap_procrustes_rigidify(ptr(p), ptr(c), ptr(cu), B * P, ptr(out), ptr(n), float(w_rigid), float(w_noise), stream_ptr()),
+    check(lib.rap_procrustes_rigidify(ptr(p), ptr(c), ptr(cu), B * P, p.shape[0], ptr(out), ptr(n), float(w_rigid), float(w_noise), stream_ptr()),
           "rap_procrustes_rigidify")
     return out.view(prediction.shape)

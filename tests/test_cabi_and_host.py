@@ -197,7 +197,7 @@ def test_argument_validation_needs_no_gpu():
     assert L.rap_segment_nn(None, None, None, 1, None, None, None, None) == -22
     T = (C.c_double * 16)(*([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0.5, 0, 0, 1]))                 # not affine
     assert L.rap_apply_transform(1, 10, 0, T, 1, None) == -22 and b"affine" in L.rap_last_error()
-    assert L.rap_procrustes_fit_sse(None, None, None, None, 1, None, None, None, None) == -22
+    assert L.rap_procrustes_fit_sse(None, None, None, None, 1, 0, None, None, None, None) == -22
     assert L.rap_fmha_schedule(None, 1, 8, 0, None, 0, None, None) == -22
 
 

@@ -21,7 +21,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import rap_oracle as orc  # noqa: E402
-from oracle.make_golden import CASES  # noqa: E402
+from oracle.make_golden import BIG_CASES, CASES, case_params  # noqa: E402
 from rap_b200.synth import DiTConfig, make_batch, make_state_dict  # noqa: E402
 
 FWD_MAX, FWD_MEAN, SMP_MEAN_CAP = 3e-2, 4e-3, 2e-2
@@ -47,10 +47,10 @@ def _stats(a, b):
     return d.max().item(), d.mean().item()
 
 
-@pytest.mark.parametrize("name", ["ragged_b2_v3_L2_s3_rigid", "cfg1_2x512_s5"])
+@pytest.mark.parametrize("name", ["ragged_b2_v3_L2_s3_rigid", "cfg1_2x512_s5", "cfg2_2x4096_s20", "cfg3_4x4096_s3_rigid", "cfg1_2x512_s5_p512"])
 def test_forward_vs_reference_golden(golden_dir, name):
-    L, B, V, N, _, _ = CASES[name]
-    b = make_batch(B, V, N, max_parts=V + 2).to("cuda")
+    L, B, V, N, _, _, P, _ = case_params(name)
+    b = make_batch(B, V, N, max_parts=P).to("cuda")
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     m = _model(L)
     out = m(x=b.x_1, timesteps=torch.from_numpy(g["fwd_timesteps"]).cuda(), cond_coord=b.cond, local_features=b.features,
@@ -159,6 +159,59 @@ def test_sampler_vs_reference_golden(golden_dir, name):
         sampler.get_sampler("rk4")
 
 
+@pytest.mark.parametrize("name", list(BIG_CASES))
+def test_sampler_vs_reference_golden_baseline_sizes(golden_dir, name):
+    """The configurations bench.py quotes, against the reference run verbatim (oracle/make_golden.py BIG_CASES): cfg2 = 2 x 4096 points,
+    all 20 flow steps; cfg3 = 4 x 4096 with rigidity forcing; cfg1 padded to `max_parts: 512` (RAP_inference.yaml:33); 70 flow steps
+    (more than one 64-thread block of timesteps).  Same k=2 rule as above, on the trajectory steps the compact goldens keep."""
+    from rap_b200.rectified_point_flow import procrustes, sampler
+    L, B, V, N, S, rigid, P, keep = case_params(name)
+    b = make_batch(B, V, N, max_parts=P).to("cuda")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    keep = list(keep)
+    model = _model(L)
+    ctx = dict(model=model, cond=b.cond, local_features=b.features, scales=b.scales, anchor_indices=b.anchor_indices,
+               cu_seqlens_batch=b.cu_seqlens_batch, cu_seqlens_part=b.cu_seqlens_part)
+
+    def fn(x, t):        # opaque-route fallback; the fused route reads `rap_context`
+        return model(x=x, timesteps=torch.full((B,), t, device=x.device), cond_coord=b.cond, local_features=b.features, latent_features=None,
+                     scales=b.scales, anchor_indices=b.anchor_indices, cu_seqlens_batch=b.cu_seqlens_batch, cu_seqlens_part=b.cu_seqlens_part)
+    fn.rap_context = ctx
+    res = sampler.get_sampler("euler")(flow_model_fn=fn, x_1=b.x_1, x_0=b.cond, condition=b.cond, points_per_part=b.points_per_part,
+                                       cu_seqlens_batch=b.cu_seqlens_batch, anchor_indices=b.anchor_indices, num_steps=S, return_trajectory=True,
+                                       rigidity_forcing=rigid, return_end_point_trajectory=True)
+    _check_clean()
+    # fp16-autocast emulation of the reference's GPU numerics with the same oracle code (torch on the GPU)
+    sd16 = {k: v.cuda() for k, v in make_state_dict(DiTConfig(num_layers=L)).items()}
+    cu_b_host, cu_p_host, ppp_host = b.cu_seqlens_batch.cpu(), b.cu_seqlens_part.cpu(), b.points_per_part.cpu()
+
+    def fn16(x, t):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return orc.dit_forward(sd16, x, torch.full((B,), t, device="cuda"), b.cond, b.features, b.scales, b.anchor_indices, cu_b_host, cu_p_host).float()
+    ep16, tr16 = orc.flow_sampler(fn16, b.x_1, b.cond, ppp_host, S, rigid)
+    worst = 0.0
+    for key, a16 in (("end_point_trajectory", ep16), ("trajectory", tr16)):
+        assert res[key].shape == (S, b.cond.shape[0], 3)
+        mx, mean = _stats(res[key][keep], g[key])
+        amx, amean = _stats(a16[keep], g[key])
+        print(f"[{name}] {key} (steps {keep}): ours max {mx:.2e} mean {mean:.2e} | fp16-autocast oracle max {amx:.2e} mean {amean:.2e}")
+        assert mx <= 2 * amx + 5e-3 and mean <= 2 * amean + 1e-3 and mean <= SMP_MEAN_CAP
+        worst = max(worst, amx)
+    pred = res["end_point_trajectory"][-1]
+    R, t = procrustes.fit_transformations(b.cond, pred, b.points_per_part, b.cu_seqlens_batch)
+    assert R.shape == (B, P, 3, 3) and t.shape == (B, P, 3)
+    Rg, tg = torch.from_numpy(g["rotations"]).cuda(), torch.from_numpy(g["translations"]).cuda()
+    for bb, p, s, e in orc.part_offsets(ppp_host):
+        mine = b.cond[s:e] @ R[bb, p].t() + t[bb, p]
+        ref = b.cond[s:e] @ Rg[bb, p].t() + tg[bb, p]
+        assert (mine - ref).abs().max().item() <= 2 * worst + 5e-3
+    empty = (b.points_per_part == 0)
+    assert R[empty].abs().max().item() == 0 and t[empty].abs().max().item() == 0      # procrustes.py:71-76
+    rig = procrustes.rigidify_prediction_with_procrustes(torch.from_numpy(g["end_point_trajectory"][-1]).cuda(), b.cond, b.points_per_part,
+                                                         b.cu_seqlens_batch)
+    assert (rig.cpu() - torch.from_numpy(g["rigidified"])).abs().max().item() < 5e-4   # same input as the reference: tight
+
+
 def test_full_size_properties_cfg2():
     """BASELINE cfg2 shape (2 x 4096 points): size-independent properties of the CUDA path.
     (1) scenes in a packed batch do not interact: batch of two == each scene alone;
@@ -180,3 +233,36 @@ def test_full_size_properties_cfg2():
     vp = m(**kw(onep, onep.x_1, ts[:1]))
     _check_clean()
     assert (vp - v1[perm]).abs().max().item() < 5e-3
+
+
+def test_register_sharded_micro_batches_equal_the_whole_batch():
+    """`Registrar.register_sharded` on one rank: micro-batching to a point budget (RAP_inference.yaml:36) must not change any scene's
+    result (scenes never interact), poses come back as (B,P,12) in scene order, and `wait=False` hands back device tensors."""
+    from rap_b200.engine import Registrar
+    sd = make_state_dict(DiTConfig(num_layers=2), seed=0)
+    reg = Registrar(sd, num_layers=2, device="cuda", num_steps=3, rigidity_forcing=True)
+    host = make_batch(3, 2, [300, 212], max_parts=3)
+    whole = reg.register_host(host)
+    sh = reg.register_sharded(host, max_points_per_batch=1100)          # 512 points per scene -> micro-batches of 2 + 1 scenes
+    _check_clean()
+    assert sh.scene_range == range(0, 3) and sh.poses.shape == (3, 3, 12) and not sh.points.is_cuda
+    assert (sh.points - whole.points).abs().max().item() < 2e-3
+    assert (sh.rotations - whole.rotations).abs().max().item() < 2e-3 and (sh.translations - whole.translations).abs().max().item() < 2e-3
+    dev = reg.register_sharded(host.to("cuda"), wait=False).wait()
+    assert dev.poses.is_cuda and (dev.poses.cpu() - sh.poses).abs().max().item() < 2e-3
+
+
+def test_procrustes_part_table_past_the_cloud_is_refused_on_the_device():
+    """The reference asserts sum(points_per_part) == N on the host (utils/point_clouds.py:41-44).  A device-resident table is not read
+    back here; the kernel skips parts that reach past the cloud (no out-of-bounds access) and flags them."""
+    from rap_b200 import _lib
+    from rap_b200.rectified_point_flow import procrustes
+    src, tgt = torch.randn(100, 3, device="cuda"), torch.randn(100, 3, device="cuda")
+    ppp_bad = torch.tensor([[60, 70]], device="cuda")                    # 130 > 100 points
+    R, t = procrustes.fit_transformations(src, tgt, ppp_bad, torch.tensor([0, 100], device="cuda"))
+    torch.cuda.synchronize()
+    assert (_lib.device_error() & 0xff) == 0xB1
+    assert R[0, 1].abs().max().item() == 0 and torch.isfinite(R[0, 0]).all()     # the in-bounds part was fitted, the other one skipped
+    with pytest.raises(ValueError):                                              # a host-resident table is checked like the reference does
+        procrustes.fit_transformations(src, tgt, ppp_bad.cpu(), torch.tensor([0, 100]))
+    assert _lib.device_error() == 0
