@@ -232,7 +232,7 @@ def comparators_block(dev, sd, d, plan, reg) -> dict:
     seg = {"per_view": [0, PTS, 2 * PTS], "per_scene": [0, T]}
     own = own_kernel_comparators(dev)
     att = cmp.attention_comparators(T, seg)
-    if os.environ.get("RAP_BENCH_FLASHINFER", "1") != "0":
+    if os.environ.get("RAP_BENCH_FLASHINFER", "0") == "1":   # JIT-compiles a CUTLASS FMHA with nvcc on first use (minutes on a fresh box): opt-in
         fi = cmp.flashinfer_comparator(T, seg, timeout_s=float(os.environ.get("RAP_BENCH_FLASHINFER_TIMEOUT", "150")))
         for k in seg:
             att[k].update(fi.get(k, {}) if "error" not in fi else {"flashinfer_error": fi["error"]})

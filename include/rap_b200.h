@@ -146,6 +146,13 @@ int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_seqlens_
 int rap_fmha_schedule(const int32_t* cu_seqlens_host, int n_segments, int heads, int force_split, int32_t* items_out, int capacity,
                       int* n_slots_out, int* max_pieces_out);
 
+/* Host-only helper (no GPU): the PERSISTENT attention schedule the product launches by default -- one CTA per SM, each walking a contiguous,
+ * equal-cost range of the linearised (query block x head, key block) space; units that straddle a CTA boundary are cut along the keys and
+ * recombined by the piece that finishes last.  items as above, ordered by CTA; cta_ptr_out[n_ctas_used + 1] = item range of every CTA.
+ * n_ctas <= 0: the SM count of the current device (148 without one).  Returns the number of items. */
+int rap_fmha_schedule_persistent(const int32_t* cu_seqlens_host, int n_segments, int heads, int n_ctas, int force_split, int32_t* items_out,
+                                 int capacity, int32_t* cta_ptr_out, int cta_capacity, int* n_ctas_out, int* n_slots_out, int* max_pieces_out);
+
 /* Host-only helper (no GPU): the 3x3 Kabsch solve used by the kernel, for CPU unit tests. */
 int rap_kabsch_host(const double* H9, double* R9);
 

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "rap_apply_transform": (C.c_int, [_vp, C.c_longlong, C.c_int, C.POINTER(C.c_double), _vp, _vp]),
     "rap_bench_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int, C.POINTER(C.c_float)]),
     "rap_fmha_schedule": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rap_fmha_schedule_persistent": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                               C.POINTER(C.c_int)]),
     "rap_test_spinnet_patches": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.c_int, C.c_float, _f32p, _vp]),
     "rap_kabsch_host": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rap_launch_count": (C.c_int64, []),

@@ -356,7 +356,8 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
 struct rap_plan {
     rap_dit* dit = nullptr;
     int T = 0, B = 0, P = 0, VP = 0, n_cap = 0;
-    int n_items_part = 0, n_items_batch = 0, fmha_pieces_part = 0, fmha_pieces_batch = 0;
+    int n_items_part = 0, n_items_batch = 0, fmha_pieces_part = 0, fmha_pieces_batch = 0;   // n_items_*: grid of the launch (CTAs)
+    int *cta_ptr_part = nullptr, *cta_ptr_batch = nullptr;   // persistent attention schedule: item range of every CTA (null: one item per CTA)
     char* ws = nullptr;
     // layout
     int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr, *zero_rows = nullptr;
@@ -403,7 +404,7 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
         RAP_REQUIRE(sum == cu_b[b + 1] - cu_b[b], "rap_plan_create: sum(points_per_part[%d])=%d != scene length %d", b, sum, cu_b[b + 1] - cu_b[b]);
         for (int i = cu_b[b]; i < cu_b[b + 1]; ++i) scene_of_tok[i] = b;
     }
-    const FmhaSchedule sp = build_fmha_schedule(cu_part, HEADS), sb = build_fmha_schedule(cu_batch, HEADS);
+    const FmhaSchedule sp = build_fmha_schedule_auto(cu_part, HEADS), sb = build_fmha_schedule_auto(cu_batch, HEADS);
     const std::vector<FmhaItem>&tp = sp.items, &tb = sb.items;
     const size_t fmha_ws_floats = std::max(sp.workspace_floats(), sb.workspace_floats());
     const size_t fmha_slots = (size_t)std::max(sp.n_slots, sb.n_slots);
@@ -411,12 +412,12 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     rap_plan* pl = new rap_plan();
     pl->dit = dit; pl->T = T; pl->B = n_scenes; pl->P = max_parts; pl->VP = (int)slot.size();
     pl->n_cap = std::max(std::max(max_timesteps, n_scenes), 1);
-    pl->n_items_part = (int)tp.size(); pl->n_items_batch = (int)tb.size(); pl->fmha_pieces_part = sp.max_pieces; pl->fmha_pieces_batch = sb.max_pieces;
+    pl->n_items_part = sp.n_ctas(); pl->n_items_batch = sb.n_ctas(); pl->fmha_pieces_part = sp.max_pieces; pl->fmha_pieces_batch = sb.max_pieces;
     const int M = dit->M;
     const size_t Tp = (size_t)((T + 127) / 128) * 128;     // padded rows so tail tiles stay in-bounds for plain loads/stores
     size_t bytes = 0;
     auto need = [&](size_t n) { bytes = ((bytes + 255) & ~size_t(255)) + n; };
-    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(4 * (size_t)T); need(sizeof(FmhaItem) * tp.size()); need(sizeof(FmhaItem) * tb.size());
+    need(4 * cu_part.size()); need(4 * slot.size() + 4); need(4 * (size_t)T); need(4 * (size_t)T); need(sizeof(FmhaItem) * tp.size()); need(sizeof(FmhaItem) * tb.size()); need(4 * sp.cta_ptr.size() + 4); need(4 * sb.cta_ptr.size() + 4);
     need(4 * fmha_ws_floats); need(4 * fmha_slots + 4);
     need(4 * Tp * D); need(4 * Tp * D); need(4 * Tp * 3); need(4 * (size_t)pl->n_cap);
     need(2 * Tp * D); need(2 * Tp * D); need(2 * Tp * 3 * D); need(2 * Tp * FF_INNER); need(2 * Tp * 128); need(2 * Tp * 64);
@@ -428,6 +429,8 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     Slab s; s.base = pl->ws; s.size = bytes;
     pl->cu_part = s.take<int>(cu_part.size()); pl->slot = s.take<int>(slot.size() + 1); pl->scene_of_tok = s.take<int>(T); pl->zero_rows = s.take<int>(T);
     pl->items_part = s.take<FmhaItem>(tp.size()); pl->items_batch = s.take<FmhaItem>(tb.size());
+    if (!sp.cta_ptr.empty()) pl->cta_ptr_part = s.take<int>(sp.cta_ptr.size());
+    if (!sb.cta_ptr.empty()) pl->cta_ptr_batch = s.take<int>(sb.cta_ptr.size());
     pl->fmha_ws = s.take<float>(fmha_ws_floats); pl->fmha_counters = s.take<int>(fmha_slots + 1);
     pl->h = s.take<float>(Tp * D); pl->x16 = s.take<__half>(Tp * D);       // adjacent: one L2 persistence window covers the residual stream
     pl->resid_bytes = (size_t)(reinterpret_cast<char*>(pl->x16 + Tp * D) - reinterpret_cast<char*>(pl->h));
@@ -444,6 +447,8 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     if (e == cudaSuccess) e = up(pl->scene_of_tok, scene_of_tok.data(), 4 * (size_t)T);
     if (e == cudaSuccess) e = up(pl->items_part, tp.data(), sizeof(FmhaItem) * tp.size());
     if (e == cudaSuccess) e = up(pl->items_batch, tb.data(), sizeof(FmhaItem) * tb.size());
+    if (e == cudaSuccess && pl->cta_ptr_part) e = up(pl->cta_ptr_part, sp.cta_ptr.data(), 4 * sp.cta_ptr.size());
+    if (e == cudaSuccess && pl->cta_ptr_batch) e = up(pl->cta_ptr_batch, sb.cta_ptr.data(), 4 * sb.cta_ptr.size());
     int rc = e == cudaSuccess ? RAP_OK : fail(RAP_ECUDA, "rap_plan_create: upload failed: %s", cudaGetErrorString(e));
     // A-operand tensor maps (rows = T so out-of-range rows of the last tile are zero-filled by TMA)
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_x16, pl->x16, T, D, D, 128);
@@ -556,7 +561,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
             FmhaArgs f{};
-            f.items = b == 0 ? pl->items_part : pl->items_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;
+            f.items = b == 0 ? pl->items_part : pl->items_batch; f.cta_ptr = b == 0 ? pl->cta_ptr_part : pl->cta_ptr_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;
             f.ws_pieces = b == 0 ? pl->fmha_pieces_part : pl->fmha_pieces_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
             f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
@@ -692,58 +697,88 @@ extern "C" int rap_fmha_schedule(const int32_t* cu_host, int n_segments, int hea
 }
 
 // Timing aid: `iters` back-to-back launches of one attention call between two events (schedule built once, like a plan does).
+namespace {
+// Device copy of an attention schedule for the micro entry points (a plan holds the same data for the product path).
+struct DevSchedule {
+    FmhaItem* items = nullptr; int* cta_ptr = nullptr; float* ws = nullptr; int* counters = nullptr;
+    int upload(const FmhaSchedule& sch) {
+        RAP_CUDA(cudaMalloc(&items, sizeof(FmhaItem) * std::max<size_t>(sch.items.size(), 1)));
+        RAP_CUDA(cudaMemcpy(items, sch.items.data(), sizeof(FmhaItem) * sch.items.size(), cudaMemcpyHostToDevice));
+        if (!sch.cta_ptr.empty()) {
+            RAP_CUDA(cudaMalloc(&cta_ptr, 4 * sch.cta_ptr.size()));
+            RAP_CUDA(cudaMemcpy(cta_ptr, sch.cta_ptr.data(), 4 * sch.cta_ptr.size(), cudaMemcpyHostToDevice));
+        }
+        RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
+        RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
+        RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
+        return RAP_OK;
+    }
+    ~DevSchedule() { cudaFree(items); cudaFree(cta_ptr); cudaFree(ws); cudaFree(counters); }
+};
+}  // namespace
+
+// Host-only: the persistent ("stream-K") attention schedule for segments cu[0..n] on n_ctas CTAs (<= 0: one per SM of the current device,
+// 148 without a device).  items as in rap_fmha_schedule; cta_ptr_out[n_ctas_used + 1] = item range of every CTA.  Returns the item count.
+extern "C" int rap_fmha_schedule_persistent(const int32_t* cu_host, int n_segments, int heads, int n_ctas, int force_split, int32_t* items_out,
+                                            int capacity, int32_t* cta_ptr_out, int cta_capacity, int* n_ctas_out, int* n_slots_out, int* max_pieces_out) {
+    RAP_REQUIRE(cu_host && n_segments >= 1 && heads >= 1, "rap_fmha_schedule_persistent: bad argument");
+    const FmhaSchedule sch = build_fmha_schedule_persistent(std::vector<int>(cu_host, cu_host + n_segments + 1), heads, n_ctas, force_split != 0);
+    if (n_ctas_out) *n_ctas_out = sch.n_ctas();
+    if (n_slots_out) *n_slots_out = sch.n_slots;
+    if (max_pieces_out) *max_pieces_out = sch.max_pieces;
+    if (items_out) {
+        RAP_REQUIRE((size_t)capacity >= sch.items.size(), "rap_fmha_schedule_persistent: capacity %d < %zu items", capacity, sch.items.size());
+        memcpy(items_out, sch.items.data(), sizeof(FmhaItem) * sch.items.size());
+    }
+    if (cta_ptr_out) {
+        RAP_REQUIRE((size_t)cta_capacity >= sch.cta_ptr.size(), "rap_fmha_schedule_persistent: cta capacity %d < %zu", cta_capacity, sch.cta_ptr.size());
+        memcpy(cta_ptr_out, sch.cta_ptr.data(), 4 * sch.cta_ptr.size());
+    }
+    return (int)sch.items.size();
+}
+
+// Timing aid: `iters` back-to-back launches of one attention call between two events (schedule built once, like a plan does).
 extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, float* ms_per_launch) {
     RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch, "rap_bench_fmha: bad argument");
-    const FmhaSchedule sch = build_fmha_schedule(std::vector<int>(cu_host, cu_host + n_segments + 1), heads);
-    FmhaItem* dt = nullptr; float* ws = nullptr; int* counters = nullptr;
-    RAP_CUDA(cudaMalloc(&dt, sizeof(FmhaItem) * sch.items.size()));
-    RAP_CUDA(cudaMemcpy(dt, sch.items.data(), sizeof(FmhaItem) * sch.items.size(), cudaMemcpyHostToDevice));
-    RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
-    RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
-    RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
+    const FmhaSchedule sch = build_fmha_schedule_auto(std::vector<int>(cu_host, cu_host + n_segments + 1), heads);
+    DevSchedule ds;
+    RAP_TRY(ds.upload(sch));
     CUtensorMap tm;
     RAP_TRY(make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128));
     FmhaArgs f{};
-    f.items = dt; f.ws = ws; f.counters = counters; f.ws_pieces = sch.max_pieces;
+    f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
     f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = RAP_OK;
-    for (int i = 0; i < 3 && !rc; ++i) rc = launch_fmha(tm, f, (int)sch.items.size(), nullptr);
+    for (int i = 0; i < 3 && !rc; ++i) rc = launch_fmha(tm, f, sch.n_ctas(), nullptr);
     cudaEventRecord(e0, nullptr);
-    for (int i = 0; i < iters && !rc; ++i) rc = launch_fmha(tm, f, (int)sch.items.size(), nullptr);
+    for (int i = 0; i < iters && !rc; ++i) rc = launch_fmha(tm, f, sch.n_ctas(), nullptr);
     cudaEventRecord(e1, nullptr);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(ms_per_launch, e0, e1);
     *ms_per_launch /= iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(dt); cudaFree(ws); cudaFree(counters);
     return rc;
 }
 
 extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, int force_split, void* out, void* dbg, void* stream) {
     RAP_REQUIRE(heads == HEADS, "rap_test_fmha: heads must be 8");
     std::vector<int> cu(cu_host, cu_host + n_segments + 1);
-    const FmhaSchedule sch = build_fmha_schedule(cu, heads, force_split != 0);
-    FmhaItem* dt = nullptr;
-    float* ws = nullptr;
-    int* counters = nullptr;
-    RAP_CUDA(cudaMalloc(&dt, sizeof(FmhaItem) * sch.items.size()));
-    RAP_CUDA(cudaMemcpy(dt, sch.items.data(), sizeof(FmhaItem) * sch.items.size(), cudaMemcpyHostToDevice));
-    RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
-    RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
-    RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
+    // force_split = 2: the one-item-per-CTA kernel with its last wave split (the A/B variant), whatever RAP_FMHA_PERSIST says
+    const FmhaSchedule sch = force_split == 2 ? build_fmha_schedule(cu, heads, true) : build_fmha_schedule_auto(cu, heads, force_split != 0);
+    DevSchedule ds;
+    RAP_TRY(ds.upload(sch));
     CUtensorMap tm;
     int rc = make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128);
     if (!rc) {
         FmhaArgs f{};
-        f.items = dt; f.ws = ws; f.counters = counters; f.ws_pieces = sch.max_pieces;
+        f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
         f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
-        rc = launch_fmha(tm, f, (int)sch.items.size(), static_cast<cudaStream_t>(stream));
-        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, (int)sch.items.size(), static_cast<cudaStream_t>(stream));   // counters must have reset themselves
+        rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));
+        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));   // counters must have reset themselves
     }
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-    cudaFree(dt); cudaFree(ws); cudaFree(counters);
     return rc;
 }
 

@@ -395,6 +395,357 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+
+// ======================================================================================= persistent (stream-K) variant
+// Same per-block pipeline as fmha_kernel<2>, but ONE CTA per SM walks a list of items (FmhaSchedule::cta_ptr): barriers, TMEM and the
+// K/V ring are set up once and keep running across items.  Phase bookkeeping is by running counters instead of the block index:
+//   cq[t] QK^T issues / cp[t] P.V issues on tile t (UMMA warp), cs blocks consumed (softmax warps of tile t), n items (Q buffer).
+// Hand-over rules at an item boundary (everything else is the steady-state protocol):
+//   * Q tiles of item n+1 are loaded once the last QK^T of item n has retired (q_empty, committed behind it);
+//   * QK^T(0) of item n+1 waits, like any QK^T, for s_free of the tile's previous block (the last block of item n);
+//   * P.V(0) of item n+1 overwrites O (accumulate = 0): it waits for p_full, which the softmax warps only signal after their epilogue of
+//     item n has read O out of TMEM (program order in those warps), so no extra barrier is needed.
+// No CTA ever waits for another CTA: split units only publish partial rows, the piece that arrives last combines them.
+__global__ void __launch_bounds__(FCfg<2>::kThreads, 1)
+fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
+    using F = FCfg<2>;
+    constexpr int NT = 2;
+    constexpr int KV_STAGES = F::KV_STAGES, OFF_Q = F::OFF_Q, OFF_K = F::OFF_K, OFF_V = F::OFF_V, OFF_BAR = F::OFF_BAR;
+    constexpr uint32_t TMEM_COLS = F::TMEM_COLS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int it0 = p.cta_ptr[blockIdx.x], it1 = p.cta_ptr[blockIdx.x + 1];      // plan data, not produced by the previous kernel
+
+    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t q_full = bar;
+    auto k_full = [&](int s) { return bar + 8 + 8 * s; };
+    auto k_empty = [&](int s) { return bar + 40 + 8 * s; };
+    auto v_full = [&](int s) { return bar + 72 + 8 * s; };
+    auto v_empty = [&](int s) { return bar + 104 + 8 * s; };
+    auto s_full = [&](int t) { return bar + 136 + 8 * t; };
+    auto p_full = [&](int t) { return bar + 152 + 8 * t; };
+    auto pv_done = [&](int t) { return bar + 168 + 8 * t; };
+    auto s_free = [&](int t) { return bar + 184 + 8 * t; };
+    const uint32_t tmem_slot = bar + 200;
+    const uint32_t q_empty = bar + 216;
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023u) { atomicCAS(&g_dev_error, 0u, 0xA1u); __trap(); }
+        tma_prefetch_desc(&tm_qkv);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 200);
+    pdl_wait();                                    // qkv comes from the previous kernel
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        const bool leader = elect_one();
+        int s = 0; uint32_t ph = 0;
+        for (int it = it0, n = 0; it < it1; ++it, ++n) {
+            const FmhaItem item = p.items[it];
+            const int q0 = item.q_row0, kv_begin = item.kv_lo;
+            const int n_kv = (item.kv_hi - kv_begin + BKV - 1) / BKV;
+            const bool two = q0 + BQ < item.seg_end;
+            const int col_q = item.head * HD, col_k = p.d_model + item.head * HD, col_v = 2 * p.d_model + item.head * HD;
+            if (n > 0) mbar_wait(q_empty, (n - 1) & 1, 0x40);          // every QK^T of the previous item has read its Q tiles
+            if (leader) {
+                mbar_expect_tx(q_full, two ? 2 * TILE_BYTES : TILE_BYTES);
+                tma_load_2d(sbase + OFF_Q, &tm_qkv, q_full, col_q, q0);
+                if (two) tma_load_2d(sbase + OFF_Q + TILE_BYTES, &tm_qkv, q_full, col_q, q0 + BQ);
+            }
+            for (int j = 0; j < n_kv; ++j) {
+                const int row = kv_begin + j * BKV;
+                mbar_wait(k_empty(s), ph ^ 1, 0x41);
+                if (leader) {
+                    mbar_expect_tx(k_full(s), TILE_BYTES);
+                    tma_load_2d(sbase + OFF_K + s * TILE_BYTES, &tm_qkv, k_full(s), col_k, row);
+                }
+                mbar_wait(v_empty(s), ph ^ 1, 0x42);
+                if (leader) {
+                    mbar_expect_tx(v_full(s), TILE_BYTES);
+                    tma_load_2d(sbase + OFF_V + s * TILE_BYTES, &tm_qkv, v_full(s), col_v, row);
+                }
+                if (++s == KV_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ UMMA issuer (warp converged, one elected lane issues)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV, false, false);   // A=Q K-major, B=K K-major, N=128
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A=P K-major, B=V MN-major, N=64
+        auto issue_qk = [&](int t, int s) {
+            const uint64_t dq = umma_desc_sw128(sbase + OFF_Q + t * TILE_BYTES, 1024);
+            const uint64_t dk = umma_desc_sw128(sbase + OFF_K + s * TILE_BYTES, 1024);
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem + t * TM_TILE + TM_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                umma_commit(s_full(t));
+            }
+        };
+        int s = 0; uint32_t ph = 0;                      // K/V ring position of the current block
+        uint32_t cq[2] = {0, 0}, cp[2] = {0, 0};
+        for (int it = it0, n = 0; it < it1; ++it, ++n) {
+            const FmhaItem item = p.items[it];
+            const int n_kv = (item.kv_hi - item.kv_lo + BKV - 1) / BKV;
+            const int nt = (item.q_row0 + BQ < item.seg_end) ? 2 : 1;
+            mbar_wait(q_full, n & 1, 0x50);
+            mbar_wait(k_full(s), ph, 0x51);
+            for (int t = 0; t < nt; ++t) {
+                if (cq[t] > 0) mbar_wait(s_free(t), (cq[t] - 1) & 1, 0x56);     // the tile's previous block (of the previous item) is consumed
+                tc_fence_after();
+                issue_qk(t, s);
+                ++cq[t];
+            }
+            if (leader) { umma_commit(k_empty(s)); if (n_kv == 1) umma_commit(q_empty); }
+            for (int j = 0; j < n_kv; ++j) {
+                const int s1 = (s + 1 == KV_STAGES) ? 0 : s + 1;
+                const uint32_t ph1 = (s + 1 == KV_STAGES) ? ph ^ 1 : ph;
+                const bool more = j + 1 < n_kv;
+                const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES, 1024);
+                for (int t = 0; t < nt; ++t) {
+                    if (more) {                              // next scores of this tile as soon as its softmax is done with S_t(j)
+                        if (t == 0) mbar_wait(k_full(s1), ph1, 0x53);
+                        mbar_wait(s_free(t), (cq[t] - 1) & 1, 0x55);
+                        tc_fence_after();
+                        issue_qk(t, s1);
+                        ++cq[t];
+                        if (t == nt - 1 && leader) { umma_commit(k_empty(s1)); if (j + 2 == n_kv) umma_commit(q_empty); }
+                    }
+                    if (t == 0) mbar_wait(v_full(s), ph, 0x54);
+                    mbar_wait(p_full(t), cp[t] & 1, 0x52);   // P_t(j) in TMEM, O_t rescaled if needed (j = 0: O_t of the previous item read out)
+                    tc_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < BKV / 16; ++k)   // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 rows (encoded >> 4)
+                            umma_f16_ts(tmem + t * TM_TILE + TM_O, tmem + t * TM_TILE + TM_P + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+                        umma_commit(pv_done(t));
+                        if (t == nt - 1) umma_commit(v_empty(s));
+                    }
+                    ++cp[t];
+                }
+                s = s1; ph = ph1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax + epilogue warps
+        const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
+        const int qd = warp & 3;                         // TMEM lane quarter of this warp
+        const int r = qd * 32 + lane;                    // query row inside the tile
+        const uint32_t t_lane = tmem + (uint32_t(qd * 32) << 16);
+        const uint32_t tm_s = t_lane + t * TM_TILE + TM_S, tm_p = t_lane + t * TM_TILE + TM_P, tm_o = t_lane + t * TM_TILE + TM_O;
+        const float sl2 = p.scale_log2;
+        uint32_t cs = 0;                                 // blocks of this tile consumed so far (all items)
+        uint32_t sreg[4][32];
+        for (int it = it0; it < it1; ++it) {
+            const FmhaItem item = p.items[it];
+            const int head = item.head, q0 = item.q_row0, seg_end = item.seg_end;
+            const int kv_begin = item.kv_lo, kv_end = item.kv_hi;
+            const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
+            const bool two = q0 + BQ < seg_end;
+            if (t == 1 && !two) continue;                // this item has no second tile: its barriers do not move
+            float m_run = -INFINITY, l_run = 0.f;        // m_run: reference exponent (log2 domain), only raised lazily
+            for (int j = 0; j < n_kv; ++j, ++cs) {
+                mbar_wait(s_full(t), cs & 1, 0x61);
+                tc_fence_after();
+                const int valid = kv_end - (kv_begin + j * BKV);     // columns >= valid belong to another segment
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld32(tm_s + c * 32, sreg[c]);
+                tmem_ld_wait();
+                if (valid < BKV) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) sreg[c][i] = 0xff800000u;   // -inf
+                }
+                if (j == 0) {                                        // first block: exact row max as the reference exponent
+                    float mxa[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
+                    m_run = sl2 * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+                }
+                const bool pv_ready = j == 0 || mbar_try_wait(pv_done(t), (cs - 1) & 1);   // polled here, its latency hides under the exps
+                f32x2 ls[4] = {0ull, 0ull, 0ull, 0ull};                // packed pairs: FFMA2 / FADD2 halve the issue slots around the MUFUs
+                const f32x2 sl2x2 = pack2(sl2, sl2), nmx2 = pack2(-m_run, -m_run);
+                uint32_t preg[64];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float ua, ub;
+                        unpack2(ffma2(pack2(__uint_as_float(sreg[c][i]), __uint_as_float(sreg[c][i + 1])), sl2x2, nmx2), ua, ub);
+                        const float a = ex2f(ua), b = ex2f(ub);
+                        ls[(i >> 1) & 3] = fadd2(ls[(i >> 1) & 3], pack2(a, b));
+                        preg[c * 16 + i / 2] = pack_half2(a, b);
+                    }
+                }
+                float lsum;
+                {
+                    float s0, s1;
+                    unpack2(fadd2(fadd2(ls[0], ls[1]), fadd2(ls[2], ls[3])), s0, s1);
+                    lsum = s0 + s1;
+                }
+                const bool grow = !(lsum < kRowSumLimit);            // also catches inf / NaN
+                const bool slow = __any_sync(0xffffffffu, grow);
+                if (!slow) {                                         // common case: the scores are consumed, let the tensor core
+                    tc_fence_before();                               // overwrite S_t with the next block while P_t(j) is being stored
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
+                if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(pv_done(t), (cs - 1) & 1, 0x62);   // PV_t(j-1) retired: P columns free, O stable
+                tc_fence_after();
+                if (slow) {
+                    // Rare slow path (some score exceeded the reference by ~2^15): take this block's exact row max as the new
+                    // reference, redo the block from the scores still in TMEM, and rescale O / l.
+                    float bmax = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, (c * 32 + i < valid) ? __uint_as_float(sreg[0][i]) : -INFINITY);
+                    }
+                    const float m_new = grow ? bmax * sl2 : m_run;
+                    const float alpha = ex2f(m_run - m_new);
+                    m_run = m_new;
+                    l_run *= alpha;
+                    lsum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const bool v0 = c * 32 + i < valid, v1 = c * 32 + i + 1 < valid;
+                            const float a = v0 ? ex2f(fmaf(__uint_as_float(sreg[0][i]), sl2, -m_run)) : 0.f;
+                            const float b = v1 ? ex2f(fmaf(__uint_as_float(sreg[0][i + 1]), sl2, -m_run)) : 0.f;
+                            lsum += a + b;
+                            preg[c * 16 + i / 2] = pack_half2(a, b);
+                        }
+                    }
+                    if (j > 0) {
+                        uint32_t o[8];
+#pragma unroll 1
+                        for (int c = 0; c < HD / 8; ++c) {
+                            tmem_ld8(tm_o + c * 8, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st8(tm_o + c * 8, o);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
+                l_run += lsum;
+                {   // P row -> TMEM (fp16 pairs, 64 columns): the A operand of the P.V UMMA
+                    uint32_t (&plo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&preg[0]);
+                    uint32_t (&phi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&preg[32]);
+                    tmem_st32(tm_p, plo);
+                    tmem_st32(tm_p + 32, phi);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(t));
+            }
+            // ---- item epilogue
+            mbar_wait(pv_done(t), (cs - 1) & 1, 0x63);
+            tc_fence_after();
+            const int row = q0 + t * BQ + r;
+            uint32_t o[32], o2[32];
+            tmem_ld32(tm_o, o);
+            tmem_ld32(tm_o + 32, o2);
+            tmem_ld_wait();
+            bool write_out = true;
+            if (item.slot >= 0) {
+                // Split unit: publish this piece's un-normalised row (O, reference exponent, row sum); the piece that arrives last
+                // re-references all of them to the largest exponent, adds them up in piece order and writes the output.
+                const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
+                const int nthreads = two ? 256 : 128;
+                float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
+                float4* mine = reinterpret_cast<float4*>(unit_ws + ((size_t)piece * (NT * BQ) + t * BQ + r) * kWsRow);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mine[i / 4] = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+                    mine[8 + i / 4] = make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3]));
+                }
+                mine[16] = make_float4(m_run, l_run, 0.f, 0.f);
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                if (warp == 2 && lane == 0) {
+                    const int arrived = atomicAdd(p.counters + item.slot, 1);
+                    if (arrived == n_pieces - 1) p.counters[item.slot] = 0;      // every piece has arrived: ready for the next launch
+                    *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) = arrived == n_pieces - 1;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                write_out = *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) != 0;
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");      // the flag is rewritten by this CTA's next split item
+                if (write_out) {
+                    __threadfence();
+                    const float* rows = unit_ws + (size_t)(t * BQ + r) * kWsRow;
+                    const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
+                    float m_all = -INFINITY;
+                    for (int q = 0; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
+                    l_run = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { o[i] = 0u; o2[i] = 0u; }
+                    for (int q = 0; q < n_pieces; ++q) {
+                        const float4* src = reinterpret_cast<const float4*>(rows + q * piece_stride);
+                        const float4 ml = __ldcg(src + 16);
+                        const float wq = ex2f(ml.x - m_all);
+                        l_run = fmaf(ml.y, wq, l_run);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 a = __ldcg(src + i / 4), b = __ldcg(src + 8 + i / 4);
+                            o[i] = __float_as_uint(fmaf(a.x, wq, __uint_as_float(o[i])));
+                            o[i + 1] = __float_as_uint(fmaf(a.y, wq, __uint_as_float(o[i + 1])));
+                            o[i + 2] = __float_as_uint(fmaf(a.z, wq, __uint_as_float(o[i + 2])));
+                            o[i + 3] = __float_as_uint(fmaf(a.w, wq, __uint_as_float(o[i + 3])));
+                            o2[i] = __float_as_uint(fmaf(b.x, wq, __uint_as_float(o2[i])));
+                            o2[i + 1] = __float_as_uint(fmaf(b.y, wq, __uint_as_float(o2[i + 1])));
+                            o2[i + 2] = __float_as_uint(fmaf(b.z, wq, __uint_as_float(o2[i + 2])));
+                            o2[i + 3] = __float_as_uint(fmaf(b.w, wq, __uint_as_float(o2[i + 3])));
+                        }
+                    }
+                }
+            }
+            const float inv_l = 1.0f / l_run;
+            if (write_out && row < seg_end) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    dst[i / 8] = make_uint4(pack_half2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l));
+                    dst[4 + i / 8] = make_uint4(pack_half2(__uint_as_float(o2[i]) * inv_l, __uint_as_float(o2[i + 1]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 2]) * inv_l, __uint_as_float(o2[i + 3]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 4]) * inv_l, __uint_as_float(o2[i + 5]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 6]) * inv_l, __uint_as_float(o2[i + 7]) * inv_l));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
 }  // namespace
 
 template <int NT>
@@ -488,13 +839,140 @@ FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool for
     return sch;
 }
 
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_items, cudaStream_t st) {
-    RAP_REQUIRE(n_items > 0 && a.items && a.d_model % HD == 0, "fmha: bad args (items=%d d=%d)", n_items, a.d_model);
+bool fmha_persistent_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_FMHA_PERSIST"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1 && fmha_rows_per_cta() == 256;
+}
+
+// Cost model of the persistent schedule, in units of one 128-key block of a 256-row unit (~2.5 k cycles): a unit whose second query tile
+// is empty keeps only one softmax warpgroup busy; every item pays a fixed start/drain cost (first scores, row max, epilogue, Q reload).
+namespace {
+constexpr double kOneTileBlock = 0.55, kItemOverhead = 2.0;
+constexpr int kMinPieceBlocks = 2;
+}
+
+FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int heads, int n_ctas, bool force_split) {
+    const int rows = 256;
+    int G = n_ctas > 0 ? n_ctas : num_sms();
+    struct Unit { int q, s0, s1, head, blocks; double w; };
+    std::vector<Unit> units;
+    // segment-major, then head, then query block: CTAs that run side by side read the same K/V stream out of L2
+    for (size_t s = 0; s + 1 < cu.size(); ++s)
+        for (int h = 0; h < heads; ++h)
+            for (int q = cu[s]; q < cu[s + 1]; q += rows)
+                units.push_back({q, cu[s], cu[s + 1], h, (cu[s + 1] - cu[s] + BKV - 1) / BKV, (q + BQ < cu[s + 1]) ? 1.0 : kOneTileBlock});
+    FmhaSchedule sch;
+    sch.cta_ptr.push_back(0);
+    if (units.empty()) return sch;
+    double work = 0.0;
+    for (const Unit& u : units) work += u.blocks * u.w;
+    struct Piece { int unit, b0, b1; };
+    std::vector<std::vector<Piece>> per_cta, best_cta;
+    std::vector<int> pieces_of_unit, best_pieces;
+    double best_max = 1e300;
+    const double floor_target = (force_split ? 3.0 : 6.0) + kItemOverhead;   // a CTA is not worth starting for less than a few blocks
+    size_t n_items = units.size() + (size_t)G;                               // first guess: one boundary (= one extra item) per CTA
+    if (!force_split && work + kItemOverhead * (double)units.size() <= floor_target * G) {
+        // Small launch (fewer blocks than the SMs could take a minimum share of): no cutting, whole units, longest first onto the least
+        // loaded CTA -- at most one CTA per unit.
+        std::vector<int> order(units.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return units[a].blocks * units[a].w > units[b].blocks * units[b].w; });
+        const int n = (int)std::min<size_t>((size_t)G, units.size());
+        std::vector<double> load(n, 0.0);
+        std::vector<std::vector<int>> mine(n);
+        for (int ui : order) {
+            const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            mine[c].push_back(ui);
+            load[c] += units[ui].blocks * units[ui].w + kItemOverhead;
+        }
+        for (const auto& l : mine) {
+            for (int ui : l) sch.items.push_back({units[ui].q, units[ui].s0, units[ui].s1, units[ui].head, units[ui].s0, units[ui].s1, -1, 1 << 8});
+            sch.cta_ptr.push_back((int)sch.items.size());
+        }
+        return sch;
+    }
+    for (int pass = 0; pass < 8; ++pass) {                                   // the item count feeds back into the target: keep the best pass
+        // CTA c ends where the running cost reaches (c + 1) * target: rounding to whole blocks does not accumulate towards the last CTA
+        const double target = std::max((work + kItemOverhead * (double)n_items) / G, floor_target);
+        per_cta.assign(1, {});
+        pieces_of_unit.assign(units.size(), 0);
+        double assigned = 0.0;
+        for (size_t ui = 0; ui < units.size(); ++ui) {
+            const Unit& u = units[ui];
+            int b = 0;
+            while (b < u.blocks) {
+                const bool last_cta = (int)per_cta.size() >= G;
+                const double budget = last_cta ? 1e30 : (double)per_cta.size() * target - assigned;
+                const int left = u.blocks - b;
+                int take = left;
+                if (left * u.w + kItemOverhead > budget + 0.5 * u.w) {
+                    take = (int)((budget - kItemOverhead) / u.w + 0.5);
+                    if (take > left - kMinPieceBlocks) take = left - kMinPieceBlocks;   // never leave a sliver behind ...
+                    if (take < kMinPieceBlocks) take = 0;                               // ... nor start one
+                    if (take == 0 && per_cta.back().empty()) take = left <= 2 * kMinPieceBlocks ? left : kMinPieceBlocks;
+                }
+                if (take > 0) {
+                    per_cta.back().push_back({(int)ui, b, b + take});
+                    ++pieces_of_unit[ui];
+                    assigned += take * u.w + kItemOverhead;
+                    b += take;
+                }
+                if (!last_cta && (b < u.blocks || (double)per_cta.size() * target - assigned < 0.5 * kItemOverhead + 0.5)) per_cta.emplace_back();
+            }
+        }
+        if (per_cta.back().empty()) per_cta.pop_back();
+        size_t items = 0;
+        double worst = 0.0;
+        for (const auto& l : per_cta) {
+            items += l.size();
+            double c = 0.0;
+            for (const Piece& pc : l) c += (pc.b1 - pc.b0) * units[pc.unit].w + kItemOverhead;
+            worst = std::max(worst, c);
+        }
+        if (worst < best_max) { best_max = worst; best_cta = per_cta; best_pieces = pieces_of_unit; }
+        if (items == n_items) break;
+        n_items = (items + n_items + 1) / 2;                                 // damped: plain substitution can oscillate
+    }
+    per_cta.swap(best_cta);
+    pieces_of_unit.swap(best_pieces);
+    std::vector<int> slot_of_unit(units.size(), -1), next_piece(units.size(), 0);
+    for (size_t ui = 0; ui < units.size(); ++ui)
+        if (pieces_of_unit[ui] > 1) { slot_of_unit[ui] = sch.n_slots++; sch.max_pieces = std::max(sch.max_pieces, pieces_of_unit[ui]); }
+    for (const auto& list : per_cta) {
+        for (const Piece& pc : list) {
+            const Unit& u = units[pc.unit];
+            const int lo = u.s0 + pc.b0 * BKV, hi = std::min(u.s1, u.s0 + pc.b1 * BKV);
+            sch.items.push_back({u.q, u.s0, u.s1, u.head, lo, hi, slot_of_unit[pc.unit], next_piece[pc.unit]++ | (pieces_of_unit[pc.unit] << 8)});
+        }
+        sch.cta_ptr.push_back((int)sch.items.size());
+    }
+    return sch;
+}
+
+FmhaSchedule build_fmha_schedule_auto(const std::vector<int>& cu, int heads, bool force_split) {
+    return fmha_persistent_enabled() ? build_fmha_schedule_persistent(cu, heads, 0, force_split) : build_fmha_schedule(cu, heads, force_split);
+}
+
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaStream_t st) {
+    RAP_REQUIRE(n_ctas > 0 && a.items && a.d_model % HD == 0, "fmha: bad args (ctas=%d d=%d)", n_ctas, a.d_model);
+    if (a.cta_ptr) {
+        static bool configured = false;
+        if (!configured) {
+            RAP_CUDA(cudaFuncSetAttribute(fmha_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<2>::SMEM_BYTES));
+            configured = true;
+        }
+        ProfScope _ps(KC_FMHA, st);
+        RAP_CUDA(launch_pdl(fmha_persist_kernel, dim3(n_ctas), dim3(FCfg<2>::kThreads), FCfg<2>::SMEM_BYTES, st, tm_qkv, a));
+        note_launch();
+        return RAP_OK;
+    }
     static int early = -1;
     if (early < 0) { const char* e = getenv("RAP_FMHA_EARLY"); early = (e && atoi(e) == 1) ? 1 : 0; }
     FmhaArgs b = a;
     b.early_release = early && a.score_bound;
-    return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, b, n_items, st) : launch_t<2>(tm_qkv, b, n_items, st);
+    return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, b, n_ctas, st) : launch_t<2>(tm_qkv, b, n_ctas, st);
 }
 
 }  // namespace rap

@@ -17,9 +17,11 @@ struct FmhaItem {
 
 struct FmhaSchedule {
     std::vector<FmhaItem> items;   // launch order: whole units first (longest first), then the big pieces, then the small ones
+    std::vector<int> cta_ptr;      // persistent schedule only: CTA c walks items[cta_ptr[c] .. cta_ptr[c+1]); empty for the one-item-per-CTA kernel
     int n_slots = 0;               // units that were split
     int max_pieces = 0;            // workspace stride: pieces per slot
     size_t workspace_floats() const;
+    int n_ctas() const { return cta_ptr.empty() ? (int)items.size() : (int)cta_ptr.size() - 1; }
 };
 
 // Work list for one attention launch over segments cu[0..n] (query blocks never straddle a segment).  With split enabled (default;
@@ -27,8 +29,20 @@ struct FmhaSchedule {
 // force_split (tests): cut the last wave even where the cost model says it does not pay.
 FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool force_split = false);
 
+// Persistent ("stream-K") schedule, the default: ONE CTA per SM, each walking a contiguous range of the linearised (unit, key block)
+// space of equal estimated cost, so that every SM finishes together whatever the number of (query block, head) units is -- 256 units on
+// 148 SMs (cfg2) otherwise waste a quarter of the second wave.  A unit that straddles a CTA boundary is cut along its keys; its pieces
+// leave un-normalised partial rows in the workspace and the piece that finishes last combines them in piece order (deterministic).
+// No CTA ever waits for another one.  n_ctas <= 0: one per SM.  force_split (tests): tiny per-CTA budget so that small inputs are cut too.
+// RAP_FMHA_PERSIST=0 selects the one-item-per-CTA kernel above instead (A/B measurements).
+FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int heads, int n_ctas = 0, bool force_split = false);
+bool fmha_persistent_enabled();
+// The schedule the product uses for this layout (persistent unless disabled).
+FmhaSchedule build_fmha_schedule_auto(const std::vector<int>& cu, int heads, bool force_split = false);
+
 struct FmhaArgs {
     const FmhaItem* items;   // device copy of FmhaSchedule::items
+    const int* cta_ptr;      // device copy of FmhaSchedule::cta_ptr (persistent kernel) or null (one item per CTA)
     __half* out;         // [T, d_model] fp16, head h at columns [64h, 64h+64)
     int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
     float scale_log2;    // log2(e) / sqrt(head_dim)
@@ -43,6 +57,7 @@ struct FmhaArgs {
 // tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.
 // Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM) -- schedules must match.
 int fmha_rows_per_cta();
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_items, cudaStream_t st);
+// n_ctas = FmhaSchedule::n_ctas(): the grid (number of items for the one-item-per-CTA kernel).
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_ctas, cudaStream_t st);
 
 }  // namespace rap

@@ -217,3 +217,48 @@ def test_install_eval_patches_reference_modules():
         assert ns.metrics.compute_ecdf.__module__.endswith("eval.metrics") and "rap_b200" not in ns.metrics.compute_ecdf.__module__
     finally:
         ref_loader.unload_reference()
+
+
+def _fmha_schedule_persistent(cu, n_ctas=148, force=0, heads=8):
+    import ctypes as C
+    from rap_b200 import _lib
+    cu_a = _lib.i32_array(cu)
+    n = _lib.lib.rap_fmha_schedule_persistent(cu_a, len(cu) - 1, heads, n_ctas, force, None, 0, None, 0, None, None, None)
+    buf, cp = (C.c_int32 * (8 * n))(), (C.c_int32 * (n_ctas + 2))()
+    nc, ns, mp = C.c_int(), C.c_int(), C.c_int()
+    assert _lib.lib.rap_fmha_schedule_persistent(cu_a, len(cu) - 1, heads, n_ctas, force, buf, n, cp, n_ctas + 2, C.byref(nc), C.byref(ns), C.byref(mp)) == n
+    return np.array(buf).reshape(n, 8), np.array(cp)[:nc.value + 1], ns.value, mp.value
+
+
+@pytest.mark.parametrize("force", [0, 1])
+@pytest.mark.parametrize("cu", [[0, 4096, 8192], [0, 8192], [0, 512, 1024], [0, 16384], [0, 3000, 5000, 9000], [0, 100], [0, 130, 700, 701],
+                                [0, 4096, 8192, 12288, 16384], [0, 200, 336, 408]])
+def test_fmha_persistent_schedule_tiles_the_work_and_balances_the_ctas(cu, force):
+    """Host logic of the default attention launch (one persistent CTA per SM): the items tile (query block, head) x keys exactly once,
+    pieces of a cut unit are contiguous in the keys, share a slot and are numbered 0..n-1, every CTA owns a non-empty contiguous item range,
+    and at the BASELINE shapes no CTA carries more than 3 % above the mean estimated cost (that maximum IS the kernel's duration)."""
+    items, cta_ptr, n_slots, max_pieces = _fmha_schedule_persistent(cu, force=force)
+    assert cta_ptr[0] == 0 and cta_ptr[-1] == len(items) and (np.diff(cta_ptr) > 0).all() and len(cta_ptr) - 1 <= 148
+    seen = {}
+    for q0, s0, s1, head, lo, hi, slot, piece in items.tolist():
+        assert s0 <= q0 < s1 and s0 <= lo < hi <= s1 and (lo - s0) % 128 == 0 and (hi == s1 or (hi - s0) % 128 == 0) and (q0 - s0) % 256 == 0
+        n_p, idx = piece >> 8, piece & 0xff
+        assert (slot < 0) == (n_p == 1) and idx < n_p <= max(max_pieces, 1)
+        seen.setdefault((q0, head), []).append((lo, hi, slot, idx, n_p))
+    assert len(seen) == 8 * sum(-(-(b - a) // 256) for a, b in zip(cu[:-1], cu[1:]))
+    slots = set()
+    for (q0, head), pieces in seen.items():
+        pieces.sort()
+        seg = next((a, b) for a, b in zip(cu[:-1], cu[1:]) if a <= q0 < b)
+        assert pieces[0][0] == seg[0] and pieces[-1][1] == seg[1] and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        assert len({p[2] for p in pieces}) == 1 and [p[3] for p in pieces] == list(range(pieces[0][4]))     # piece order = key order
+        if pieces[0][2] >= 0:
+            slots.add(pieces[0][2])
+    assert slots == set(range(n_slots))
+    blocks = (items[:, 5] - items[:, 4] + 127) // 128
+    cost = blocks * np.where(items[:, 0] + 128 < items[:, 2], 1.0, 0.55) + 2.0
+    per = np.array([cost[a:b].sum() for a, b in zip(cta_ptr[:-1], cta_ptr[1:])])
+    if cu in ([0, 4096, 8192], [0, 8192], [0, 16384], [0, 4096, 8192, 12288, 16384]):
+        assert len(per) == 148 and per.max() <= 1.03 * per.mean() and n_slots > 0 and max_pieces == 2
+    if cu == [0, 512, 1024] and not force:
+        assert n_slots == 0 and len(per) == 32            # small launch: whole units, nothing is cut

@@ -86,8 +86,9 @@ def test_gemm_geglu(rap):
     assert (out16.float() - ref).abs().max().item() < 2e-2
 
 
-# force=1: the units of the last, partially filled wave are split along the keys and recombined even where the cost model would not
-@pytest.mark.parametrize("force", [0, 1])
+# force=0: the product schedule (persistent CTAs, units cut where a CTA's share ends); force=1: a tiny per-CTA share, so small inputs are
+# cut into pieces and recombined too; force=2: the one-item-per-CTA kernel with its last wave split (the RAP_FMHA_PERSIST=0 variant)
+@pytest.mark.parametrize("force", [0, 1, 2])
 @pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048], [512, 512], [2000, 1500],
                                   [4096, 4096], [8192], [16384]])
 def test_fmha_varlen(rap, lens, force):

@@ -8,7 +8,7 @@ from rap_b200.dataset_process import FeatureExtractor
 from rap_b200.dataset_process.utils.point_sampling_utils import sample_farthest_points
 from rap_b200.engine import Registrar
 from rap_b200.synth import DiTConfig, make_batch, make_raw_cloud, make_spinnet_state_dict, make_state_dict
-reg = Registrar(make_state_dict(DiTConfig(num_layers=12)), num_layers=12, device="cuda", num_steps=1, rigidity_forcing=True)
+reg = Registrar(make_state_dict(DiTConfig(num_layers=1)), num_layers=1, device="cuda", num_steps=1, rigidity_forcing=True)   # 1 layer: 3 LayerNorm launches
 d = make_batch(1, 2, 4096).to("cuda")
 plan = reg.plan_for(d.cu_seqlens_batch.cpu(), d.points_per_part.cpu())
 fx = FeatureExtractor(des_r=1.0, state_dict=make_spinnet_state_dict())

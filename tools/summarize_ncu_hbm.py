@@ -11,14 +11,14 @@ def to_bytes(v, u): return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 
 def to_us(v, u): return v * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1)
 out = [f"# {tag} -- ncu --set full, HBM-/latency-bound kernels (tools/gpu_profile_hbm.sh), 1x B200", "",
        f"GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration; peak = measured HBM copy bandwidth {peak} GB/s (MEASURED_PEAKS.json).",
-       "L2 GB/s = lts__t_bytes.sum / duration (data that is L2-resident between kernels never reaches DRAM: see the lts column before judging the dram one).",
+       "L2 GB/s = lts__t_sectors.sum x 32 B / duration (data that is L2-resident between kernels never reaches DRAM: see the lts column before judging the dram one).",
        "Under ncu every launch is cold-cache and serialised.", "",
        "| kernel | grid | us | dram read MB | dram write MB | dram GB/s | frac of HBM peak | L2 traffic MB | L2 GB/s | lts %peak | sm busy % | regs |", "|" + "---|" * 12]
 for d in r[2:]:
     name = re.sub(r"\(.*", "", d[idx["Kernel Name"]]).split("::")[-1]
     us = to_us(val(d, "gpu__time_duration.sum"), units[idx["gpu__time_duration.sum"]])
     rd = to_bytes(val(d, "dram__bytes_read.sum"), units[idx["dram__bytes_read.sum"]]); wr = to_bytes(val(d, "dram__bytes_write.sum"), units[idx["dram__bytes_write.sum"]])
-    l2 = to_bytes(val(d, "lts__t_bytes.sum"), units[idx["lts__t_bytes.sum"]]) if "lts__t_bytes.sum" in idx else float("nan")
+    l2 = val(d, "lts__t_sectors.sum") * 32.0
     gbs = (rd + wr) / us / 1e3
     out.append(f"| {name} | {d[idx['launch__grid_size']]} | {us:.1f} | {rd/1e6:.2f} | {wr/1e6:.2f} | {gbs:.0f} | {gbs/peak:.3f} | {l2/1e6:.1f} | {l2/us/1e3:.0f} | "
                f"{val(d, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {val(d, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {d[idx['launch__registers_per_thread']]} |")
