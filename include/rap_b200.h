@@ -169,6 +169,12 @@ const char* rap_profile_class_name(int kernel_class);
 /* Micro entry points used by tests/ and profiling to exercise one kernel at a time. */
 int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
                   const float* addend, float* out32, void* out16, const float* gamma, void* dbg, void* stream);
+/* The residual GEMM with the next block's LayerNorm in its epilogue (N = 512; the two CTAs of a 128-row block exchange row moments over
+ * distributed shared memory): out32 = A W^T + bias + addend, ln_out (fp16) = LN(out32) * (one_plus + ln_mul[sel]) + ln_add[sel],
+ * sel(row) = row_of_tok[row] * row_stride.  Replaces AdaptiveLayerNorm / ff_norm as separate kernels (norm.py:76, layer.py:163). */
+int rap_test_gemm_ln(int M, int K, const void* A_f16, const void* W_f16, const float* bias, const float* addend, float* out32,
+                     const float* ln_mul, const float* ln_add, const int32_t* row_of_tok, int row_stride, float one_plus, void* ln_out_f16,
+                     void* stream);
 /* dbg: optional device buffer of n_kv_blocks*16 int64 receiving a clock64() timeline of CTA (0,0), or NULL. */
 int rap_test_fmha(const void* qkv_f16, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, int force_split, void* out_f16,
                   void* dbg, void* stream);

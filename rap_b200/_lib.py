@@ -75,6 +75,7 @@ PROTOTYPES = {
     "rap_profile_classes": (C.c_int, []),
     "rap_profile_class_name": (C.c_char_p, [C.c_int]),
     "rap_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _f32p, _f32p, _vp, _f32p, _vp, _vp]),
+    "rap_test_gemm_ln": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _vp, C.c_int, C.c_float, _vp, _vp]),
     "rap_test_ln_modulate": (C.c_int, [_f32p, _vp, C.c_int, _f32p, _f32p, C.c_int, _vp, C.c_float, _vp]),
     "rap_debug_read": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "rap_test_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _vp, _vp, _vp]),

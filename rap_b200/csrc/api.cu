@@ -59,6 +59,13 @@ int f32_bn() {
     return bn;
 }
 
+// LayerNorm fused into the producing GEMM's epilogue (EPI_F32_LN, 2-CTA clusters); RAP_LN_FUSE=0 restores the separate LayerNorm kernel.
+bool ln_fused() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_LN_FUSE"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RAP_NO_PDL"); v = (e && atoi(e) == 1) ? 0 : 1; }
@@ -547,16 +554,42 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
     const int T = pl->T, M = d->M;
     const float scale_log2 = 1.4426950408889634f / 8.0f;   // log2(e) / sqrt(64)
     RAP_TRY(launch_posenc_x(x, pl->a_x, T, st));
+    const int row_stride = M * 2 * D;
+    const int* rows = per_scene ? pl->scene_of_tok : pl->zero_rows;
+    const bool fuse = ln_fused();
+    // LayerNorm of the finished residual rows as the NEXT GEMM's fp16 operand (x16), either from the producing GEMM's epilogue (default:
+    // EPI_F32_LN, no LayerNorm kernel at all) or from ln_modulate_kernel (RAP_LN_FUSE=0, A/B measurements).  `m` = AdaLN module 2*layer+blk
+    // whose [scale | shift] row modulates it, or -1 - layer for the plain affine LayerNorm in front of layer's feed-forward block.
+    auto ln_args = [&](GemmArgs& g, int m) {
+        if (m >= 0) {
+            const float* ss = pl->ada_tab + ((size_t)tab_row0 * M + m) * 2 * D;
+            g.ln_mul = ss; g.ln_add = ss + D; g.ln_row_stride = row_stride; g.ln_row_of_tok = rows; g.ln_one_plus = 1.0f;
+        } else {
+            const int l = -1 - m;
+            g.ln_mul = d->ffn_w[l]; g.ln_add = d->ffn_b[l]; g.ln_row_stride = 0; g.ln_row_of_tok = pl->zero_rows; g.ln_one_plus = 0.0f;
+        }
+        g.ln_out = pl->x16; g.ln_ld = D;
+    };
+    auto residual_gemm = [&](GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, int next_ln, bool has_next) -> int {
+        if (fuse && has_next && f32_bn() == 256) {
+            ln_args(g, next_ln);
+            return launch_gemm(EPI_F32_LN, 256, ta, tb, g, st);
+        }
+        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), ta, tb, g, st));
+        if (has_next) {
+            GemmArgs t{};
+            ln_args(t, next_ln);
+            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, t.ln_mul, t.ln_add, t.ln_row_stride, t.ln_row_of_tok, t.ln_one_plus, st));
+        }
+        return RAP_OK;
+    };
     {
         GemmArgs g{};
         g.M = T; g.N = D; g.K = 64; g.addend = pl->h_static; g.out32 = pl->h; g.ld32 = D;
-        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ax, d->tm_emb_x, g, st));
+        RAP_TRY(residual_gemm(g, pl->tm_ax, d->tm_emb_x, 0, true));                 // + LN for layer 0's part-attention block
     }
-    const int row_stride = M * 2 * D;
     for (int l = 0; l < d->L; ++l) {
         for (int b = 0; b < 2; ++b) {
-            const float* ss = pl->ada_tab + ((size_t)tab_row0 * M + (2 * l + b)) * 2 * D;
-            RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, ss, ss + D, row_stride, per_scene ? pl->scene_of_tok : pl->zero_rows, 1.0f, st));
             GemmArgs q{};
             q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
@@ -567,16 +600,16 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
-            RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_attn16, d->tm_out[b][l], o, st));
+            RAP_TRY(residual_gemm(o, pl->tm_attn16, d->tm_out[b][l], b == 0 ? 2 * l + 1 : -1 - l, true));   // + LN for the global block / the feed-forward
         }
-        RAP_TRY(launch_ln_modulate(pl->h, pl->x16, T, d->ffn_w[l], d->ffn_b[l], 0, pl->zero_rows, 0.0f, st));
         GemmArgs f1{};
         f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER;
         RAP_TRY(launch_gemm(EPI_GEGLU, 256, pl->tm_x16, d->tm_w1[l], f1, st));
         GemmArgs f2{};
         f2.M = T; f2.N = D; f2.K = FF_INNER; f2.bias = d->b2[l]; f2.addend = pl->h; f2.out32 = pl->h; f2.ld32 = D;
-        if (l == d->L - 1) { f2.out16 = pl->hh16; f2.ld16 = D; }
-        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_ffmid, d->tm_w2[l], f2, st));
+        const bool last = l == d->L - 1;
+        if (last) { f2.out16 = pl->hh16; f2.ld16 = D; }                             // the head reads a plain fp16 copy, no LayerNorm
+        RAP_TRY(residual_gemm(f2, pl->tm_ffmid, d->tm_w2[l], 2 * (l + 1), !last));  // + LN for the next layer's part-attention block
     }
     GemmArgs h0{};
     h0.M = T; h0.N = D; h0.K = D; h0.bias = d->bh0; h0.out16 = pl->y1; h0.ld16 = D;
@@ -679,6 +712,20 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
     g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
+}
+
+// EPI_F32_LN in isolation: out32 = A W^T + bias + addend (N = 512) and ln_out = LN(out32) * (one_plus + ln_mul[sel]) + ln_add[sel],
+// sel(row) = row_of_tok[row] * row_stride -- the residual GEMM with the next block's LayerNorm in its epilogue (2-CTA clusters).
+extern "C" int rap_test_gemm_ln(int M, int K, const void* A, const void* W, const float* bias, const float* addend, float* out32, const float* ln_mul,
+                                const float* ln_add, const int32_t* row_of_tok, int row_stride, float one_plus, void* ln_out, void* stream) {
+    CUtensorMap ta, tb;
+    RAP_TRY(make_tmap_f16_sw128(&ta, A, M, K, K, 128));
+    RAP_TRY(make_tmap_f16_sw128(&tb, W, D, K, K, 256));
+    GemmArgs g{};
+    g.M = M; g.N = D; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.ld32 = D;
+    g.ln_mul = ln_mul; g.ln_add = ln_add; g.ln_row_of_tok = row_of_tok; g.ln_row_stride = row_stride; g.ln_one_plus = one_plus;
+    g.ln_out = static_cast<__half*>(ln_out); g.ln_ld = D;
+    return launch_gemm(EPI_F32_LN, 256, ta, tb, g, static_cast<cudaStream_t>(stream));
 }
 
 // Host-only: the attention work list (whole units + key-split pieces of the last wave) for segments cu[0..n]; 8 ints per item

@@ -417,6 +417,8 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int it0 = p.cta_ptr[blockIdx.x], it1 = p.cta_ptr[blockIdx.x + 1];      // plan data, not produced by the previous kernel
+    long long dbg_t0 = 0, dbg_c0 = 0;
+    if (p.dbg && threadIdx.x == 64) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); dbg_c0 = clock64(); }
 
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t q_full = bar;
@@ -741,6 +743,12 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
             }
         }
     }
+    if (p.dbg && threadIdx.x == 64) {            // softmax warp 2, lane 0: [cta][4] = {start ns, end ns, cycles, SM id} (tools/fmha_cta_times.py)
+        long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.dbg[blockIdx.x * 4 + 0] = dbg_t0; p.dbg[blockIdx.x * 4 + 1] = t1; p.dbg[blockIdx.x * 4 + 2] = clock64() - dbg_c0; p.dbg[blockIdx.x * 4 + 3] = smid;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
@@ -854,7 +862,9 @@ constexpr int kMinPieceBlocks = 2;
 
 FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int heads, int n_ctas, bool force_split) {
     const int rows = 256;
-    int G = n_ctas > 0 ? n_ctas : num_sms();
+    static int env_ctas = -1;                             // RAP_FMHA_CTAS: number of persistent CTAs (measurement aid; default one per SM)
+    if (env_ctas < 0) { const char* e = getenv("RAP_FMHA_CTAS"); env_ctas = e ? atoi(e) : 0; }
+    int G = n_ctas > 0 ? n_ctas : (env_ctas > 0 ? env_ctas : num_sms());
     struct Unit { int q, s0, s1, head, blocks; double w; };
     std::vector<Unit> units;
     // segment-major, then head, then query block: CTAs that run side by side read the same K/V stream out of L2

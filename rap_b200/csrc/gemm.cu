@@ -127,6 +127,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             GEMM_TS(1);
         }
+        if constexpr (EPI == EPI_F32_LN) { __syncwarp(); cluster_arrive(); cluster_wait(); }   // every thread of the cluster takes part in the exchange barrier
     } else if (warp == 1) {
         // ------------------------------------------------------------ UMMA issuer (warp converged: descriptors stay warp-uniform)
         const bool leader = elect_one();
@@ -155,6 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             GEMM_TS(4);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (EPI == EPI_F32_LN) { __syncwarp(); cluster_arrive(); cluster_wait(); }
     } else {
         // ------------------------------------------------------------ epilogue: 8 warps.  TMEM lane quarter = warp % 4
         // (hardware rule), column half = (warp - 2) / 4, so two warps share a quarter and split the tile's columns.
@@ -183,7 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
             uint32_t r[32];
 
-            if constexpr (EPI == EPI_F32) {
+            if constexpr (EPI == EPI_F32 || EPI == EPI_F32_LN) {
                 // Residual / static-embedding rows prefetched (coalesced) BEFORE waiting for the accumulator: the loads fly
                 // under this tile's MMAs.  Layout of ad[c][it]: chunk c (32 columns), rows rr0 + 4*it, 4 columns at cc*4.
                 // All addressing is hoisted: one 64-bit base per warp and tile, the loops only add compile-time multiples of the row
@@ -213,7 +215,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(tfull_bar(acc), acc_phase, 0x31);
                 tc_fence_after();
                 if (dbg_w) GEMM_TS(6);
-                const bool extras = p.table || p.out16;      // anchor-row select (embedding GEMM) / fp16 shadow (last FF2): rare launches
+                const bool extras = (EPI == EPI_F32) && (p.table || p.out16);      // anchor-row select (embedding GEMM) / fp16 shadow (last FF2): rare launches
+                // EPI_F32_LN: per-row moments of the finished rows (rows rr0 + 4*it of this warp, this thread's 4 columns of every chunk) and a
+                // private stash of the finished values in the (now idle: one tile per CTA) pipeline stages for the normalisation pass.
+                float rs[8], rq[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
+                const uint32_t vstash = smem_base + (warp - 2) * 16384 + lane * 16;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     tmem_ld32(t_row + half * HC + c * 32, r);
@@ -230,6 +238,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float4 v = make_float4(__uint_as_float(u.x) + a.x + b.x, __uint_as_float(u.y) + a.y + b.y,
                                                          __uint_as_float(u.z) + a.z + b.z, __uint_as_float(u.w) + a.w + b.w);
                             if (4 * it < rows_left) *reinterpret_cast<float4*>(out_base + it * pitch4 + c * 32) = v;
+                            if constexpr (EPI == EPI_F32_LN) {
+                                rs[it] += (v.x + v.y) + (v.z + v.w);
+                                rq[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, rq[it]))));
+                                sts4(vstash + (c * 8 + it) * 512, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                            }
                         }
                     } else {
                         const int col = col0 + c * 32 + cc * 4;
@@ -252,6 +265,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     if (c + 2 < NCH) load_addend(ad[c & 1], c + 2);
                     __syncwarp();
+                }
+                if constexpr (EPI == EPI_F32_LN) {
+                    // ---- row moments: reduce over the 8 lanes that share a row (cc = lane & 7), publish to both CTAs of the cluster
+                    const uint32_t rank = cluster_ctarank();
+                    const uint32_t stats_local = smem_base + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;      // [4 sources][128 rows] float2 (gamma area)
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) { rs[it] += __shfl_xor_sync(0xffffffffu, rs[it], o); rq[it] += __shfl_xor_sync(0xffffffffu, rq[it], o); }
+                    if (cc == 0) {
+                        const uint32_t peer = dsmem_addr(stats_local, rank ^ 1u), mine = dsmem_addr(stats_local, rank);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const uint32_t off = ((rank * 2 + half) * 128 + q * 32 + rr0 + 4 * it) * 8;
+                            dsmem_st_f32x2(mine + off, rs[it], rq[it]);
+                            dsmem_st_f32x2(peer + off, rs[it], rq[it]);
+                        }
+                    }
+                    __syncwarp();
+                    cluster_arrive();
+                    cluster_wait();
+                    // ---- normalise + modulate the stashed values: the next GEMM's fp16 A operand
+                    float mean[8], rstd[8];
+                    size_t sel[8];
+                    bool same = true;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rloc = q * 32 + rr0 + 4 * it;
+                        float sm = 0.f, sq = 0.f;
+#pragma unroll
+                        for (int src = 0; src < 4; ++src) {
+                            float a, b2;
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b2) : "r"(stats_local + (src * 128 + rloc) * 8) : "memory");
+                            sm += a; sq += b2;
+                        }
+                        mean[it] = sm * (1.0f / 512.0f);
+                        rstd[it] = rsqrtf(fmaxf(sq * (1.0f / 512.0f) - mean[it] * mean[it], 0.f) + 1e-5f);
+                        const int row = min(m0 + rloc, p.M - 1);
+                        sel[it] = (size_t)p.ln_row_of_tok[row] * (size_t)p.ln_row_stride;
+                        same = same && sel[it] == sel[0];
+                    }
+                    same = __all_sync(0xffffffffu, same && sel[0] == __shfl_sync(0xffffffffu, sel[0], 0));
+                    __half* ln_base = p.ln_out + (size_t)(row_base + rr0) * p.ln_ld + col0 + cc * 4;
+                    const size_t lpitch4 = (size_t)4 * p.ln_ld;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int col = col0 + c * 32 + cc * 4;
+                        float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), ad4 = mu;
+                        if (same) { mu = *reinterpret_cast<const float4*>(p.ln_mul + sel[0] + col); ad4 = *reinterpret_cast<const float4*>(p.ln_add + sel[0] + col); }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const uint4 u = lds4(vstash + (c * 8 + it) * 512);
+                            if (!same) { mu = *reinterpret_cast<const float4*>(p.ln_mul + sel[it] + col); ad4 = *reinterpret_cast<const float4*>(p.ln_add + sel[it] + col); }
+                            const float g = rstd[it], mn = mean[it];
+                            const float y0 = (__uint_as_float(u.x) - mn) * g * (p.ln_one_plus + mu.x) + ad4.x;
+                            const float y1 = (__uint_as_float(u.y) - mn) * g * (p.ln_one_plus + mu.y) + ad4.y;
+                            const float y2 = (__uint_as_float(u.z) - mn) * g * (p.ln_one_plus + mu.z) + ad4.z;
+                            const float y3 = (__uint_as_float(u.w) - mn) * g * (p.ln_one_plus + mu.w) + ad4.w;
+                            if (4 * it < rows_left) *reinterpret_cast<uint2*>(ln_base + it * lpitch4 + c * 32) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+                        }
+                    }
                 }
             } else {
                 // fp16 outputs: each staging round holds 64 output columns (128 B per row).
@@ -384,8 +458,16 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
         configured = true;
     }
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    ProfScope _ps(EPI == EPI_F32 ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
+    const int grid = (EPI == EPI_F32_LN || tiles < num_sms()) ? tiles : num_sms();
+    ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
+    if constexpr (EPI == EPI_F32_LN) {
+        // one 128x256 tile per CTA, the two CTAs of a 128-row block (column halves) are a cluster: CTA rank = blockIdx.x & 1 = N-tile index
+        RAP_REQUIRE(a.N == 2 * BN && a.ln_out && a.ln_mul && a.ln_add && a.ln_row_of_tok && !a.table && !a.out16 && !a.conv_pitch,
+                    "gemm: the LayerNorm epilogue needs N = 512 and the ln_* arguments (no table / fp16 shadow / convolution)");
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        note_launch();
+        return RAP_OK;
+    }
     RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, tmA, tmB, a));
     note_launch();
     return RAP_OK;
@@ -400,6 +482,7 @@ int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& 
             case EPI_F32: return launch_t<256, EPI_F32>(tmA, tmB, a, st);
             case EPI_QKV: return launch_t<256, EPI_QKV>(tmA, tmB, a, st);
             case EPI_GEGLU: return launch_t<256, EPI_GEGLU>(tmA, tmB, a, st);
+            case EPI_F32_LN: return launch_t<256, EPI_F32_LN>(tmA, tmB, a, st);
             default: break;
         }
     } else if (BN == 128) {

@@ -13,6 +13,10 @@ enum GemmEpi : int {
     EPI_F16_SILU,    // out16 = act(acc + bias[col]), act = SiLU (args.act = 0) or ReLU (args.act = 1)
     EPI_QKV,         // per-head RMS norm * gamma * sqrt(hd) on q,k; v passthrough; out16 [M,N]
     EPI_GEGLU,       // tile cols [0,BN/2)=h, [BN/2,BN)=g (weights pre-interleaved); out16[M,N/2] = h*gelu(g)
+    EPI_F32_LN,      // EPI_F32 (bias + residual -> out32) AND the LayerNorm of the finished rows, modulated, as the next GEMM's fp16 operand:
+                     // ln_out[row] = LN(out32[row]) * (ln_one_plus + ln_mul[sel(row)]) + ln_add[sel(row)].  N must be 512 = 2 tiles of 256: the
+                     // two CTAs that own a 128-row block form a thread-block cluster and exchange per-row (sum, sum of squares) through
+                     // distributed shared memory, so no LayerNorm kernel runs between the GEMMs (norm.py:76, layer.py:163)
 };
 
 struct GemmArgs {
@@ -27,6 +31,15 @@ struct GemmArgs {
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
+    // EPI_F32_LN: modulation rows ln_mul / ln_add are selected per token, sel(row) = ln_row_of_tok[row] * ln_row_stride (AdaLN table row of the
+    // token's scene; stride 0 + an all-zero index vector for the plain affine LayerNorm in front of the feed-forward block)
+    const float* ln_mul;
+    const float* ln_add;
+    const int* ln_row_of_tok;
+    int ln_row_stride;
+    float ln_one_plus;
+    __half* ln_out;           // [M, ln_ld] fp16
+    int ln_ld;
     // Implicit 3x3 convolution (spinnet.cu): A is an activation map stored per item as (conv_h + 1) rows x conv_pitch = conv_w + 2 columns
     // of positions (azimuth halo columns hold the circular neighbours, the extra row is an all-zero separator = elevation padding of
     // this and the next item), so tap (de, da) of an output tile is the SAME 2-D TMA box shifted by de * conv_pitch + da rows: no im2col

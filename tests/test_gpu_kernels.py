@@ -48,6 +48,35 @@ def test_gemm_f32_bias_residual(rap, M, N, K, bn):
     assert err < 2e-3, f"max err {err}"
 
 
+@pytest.mark.parametrize("M,K,in_place,per_row", [(128, 64, False, False), (300, 512, True, True), (8192, 512, True, False), (1000, 2048, True, True),
+                                                  (257, 128, False, True)])
+def test_gemm_f32_layernorm_epilogue(rap, M, K, in_place, per_row):
+    """EPI_F32_LN: the residual GEMM whose epilogue also writes LN(out) * (one_plus + mul[sel(row)]) + add[sel(row)] as the next GEMM's fp16
+    operand (2-CTA clusters exchange the row moments).  in_place: addend aliases the output (the residual stream); per_row: rows select
+    different modulation rows (several scenes in one tile), and a plain affine LayerNorm (one_plus = 0, stride 0) otherwise."""
+    g = torch.Generator("cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(512, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(512, device="cuda", generator=g)
+    h = 3.0 * torch.randn(M, 512, device="cuda", generator=g) + 0.7          # non-zero mean: exercises the single-pass variance
+    ref = A.float() @ W.float().t() + bias + h
+    n_sel = 3 if per_row else 1
+    tab = torch.randn(n_sel, 2, 512, device="cuda", generator=g)
+    rows = (torch.arange(M, device="cuda") * n_sel // M).to(torch.int32) if per_row else torch.zeros(M, dtype=torch.int32, device="cuda")
+    one_plus = 1.0 if per_row else 0.0
+    out32 = h.clone() if in_place else torch.zeros(M, 512, device="cuda")
+    addend = out32 if in_place else h
+    ln_out = torch.zeros(M, 512, device="cuda", dtype=torch.float16)
+    mul, add = tab[:, 0].contiguous(), tab[:, 1].contiguous()
+    rap.check(rap.lib.rap_test_gemm_ln(M, K, A.data_ptr(), W.data_ptr(), bias.data_ptr(), addend.data_ptr(), out32.data_ptr(), mul.data_ptr(), add.data_ptr(),
+                                       rows.data_ptr(), 512 if per_row else 0, one_plus, ln_out.data_ptr(), rap.stream_ptr()), "rap_test_gemm_ln")
+    _sync_check(rap)
+    assert (out32 - ref).abs().max().item() < 2e-3
+    ln_ref = F.layer_norm(ref, (512,)) * (one_plus + mul[rows.long()]) + add[rows.long()]
+    err = (ln_out.float() - ln_ref).abs().max().item()
+    assert err < 2e-2, f"max err {err}"
+
+
 def test_gemm_silu_f16(rap):
     g = torch.Generator("cuda").manual_seed(1)
     A = torch.randn(500, 512, device="cuda", generator=g).half()
