@@ -59,10 +59,13 @@ int f32_bn() {
     return bn;
 }
 
-// LayerNorm fused into the producing GEMM's epilogue (EPI_F32_LN, 2-CTA clusters); RAP_LN_FUSE=0 restores the separate LayerNorm kernel.
+// RAP_LN_FUSE=1: LayerNorm in the producing GEMM's epilogue (EPI_F32_LN, 2-CTA clusters exchange the row moments over DSMEM) instead of
+// ln_modulate_kernel.  Implemented, parity-tested and MEASURED SLOWER (r02: 103.95 vs 100.57 ms/pair): the normalisation pass costs the
+// 8 epilogue warps of 128 CTAs ~8 us per launch where the stand-alone kernel, spread over every SM, takes 3.6 us -- these GEMMs are
+// epilogue-bound, so work moved into an epilogue lands on their critical path.  Hence off by default.
 bool ln_fused() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("RAP_LN_FUSE"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    if (v < 0) { const char* e = getenv("RAP_LN_FUSE"); v = (e && atoi(e) == 1) ? 1 : 0; }
     return v == 1;
 }
 
@@ -364,7 +367,8 @@ struct rap_plan {
     rap_dit* dit = nullptr;
     int T = 0, B = 0, P = 0, VP = 0, n_cap = 0;
     int n_items_part = 0, n_items_batch = 0, fmha_pieces_part = 0, fmha_pieces_batch = 0;   // n_items_*: grid of the launch (CTAs)
-    int *cta_ptr_part = nullptr, *cta_ptr_batch = nullptr;   // persistent attention schedule: item range of every CTA (null: one item per CTA)
+    int *cta_ptr_part = nullptr, *cta_ptr_batch = nullptr;
+    int fmha_gen = 0;              // generation number of the last attention launch on this plan's workspace (FmhaArgs::gen)   // persistent attention schedule: item range of every CTA (null: one item per CTA)
     char* ws = nullptr;
     // layout
     int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr, *zero_rows = nullptr;
@@ -597,6 +601,8 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             f.items = b == 0 ? pl->items_part : pl->items_batch; f.cta_ptr = b == 0 ? pl->cta_ptr_part : pl->cta_ptr_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;
             f.ws_pieces = b == 0 ? pl->fmha_pieces_part : pl->fmha_pieces_batch; f.out = pl->attn16; f.d_model = D; f.scale_log2 = scale_log2;
             f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
+            if (++pl->fmha_gen <= 0) pl->fmha_gen = 1;
+            f.gen = pl->fmha_gen;
             RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
@@ -798,9 +804,9 @@ extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = RAP_OK;
-    for (int i = 0; i < 3 && !rc; ++i) rc = launch_fmha(tm, f, sch.n_ctas(), nullptr);
+    for (int i = 0; i < 3 && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr); }
     cudaEventRecord(e0, nullptr);
-    for (int i = 0; i < iters && !rc; ++i) rc = launch_fmha(tm, f, sch.n_ctas(), nullptr);
+    for (int i = 0; i < iters && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr); }
     cudaEventRecord(e1, nullptr);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(ms_per_launch, e0, e1);
@@ -822,8 +828,10 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
         FmhaArgs f{};
         f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
         f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
+        f.gen = 1;
         rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));
-        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));   // counters must have reset themselves
+        f.gen = 2;                                                                                          // a second launch on the same workspace:
+        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));   // counters reset / stale row flags ignored
     }
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     return rc;

@@ -548,6 +548,10 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
         const float sl2 = p.scale_log2;
         uint32_t cs = 0;                                 // blocks of this tile consumed so far (all items)
         uint32_t sreg[4][32];
+        // optional timeline of CTA 5 (tools/fmha_cta_times.py): per item [8] = {start, block 0 done, last block done, last P.V retired,
+        // partial rows published / combined, output written, key blocks, split?}
+        const bool stamp = p.dbg && blockIdx.x == 5 && warp == 2 && lane == 0;
+#define PSTAMP(k) do { if (stamp) p.dbg[8192 + (size_t)(it - it0) * 8 + (k)] = clock64(); } while (0)
         for (int it = it0; it < it1; ++it) {
             const FmhaItem item = p.items[it];
             const int head = item.head, q0 = item.q_row0, seg_end = item.seg_end;
@@ -556,6 +560,8 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
             const bool two = q0 + BQ < seg_end;
             if (t == 1 && !two) continue;                // this item has no second tile: its barriers do not move
             float m_run = -INFINITY, l_run = 0.f;        // m_run: reference exponent (log2 domain), only raised lazily
+            PSTAMP(0);
+            if (stamp) { p.dbg[8192 + (size_t)(it - it0) * 8 + 6] = n_kv; p.dbg[8192 + (size_t)(it - it0) * 8 + 7] = item.slot >= 0 ? (item.piece & 0xff) + 1 : 0; }
             for (int j = 0; j < n_kv; ++j, ++cs) {
                 mbar_wait(s_full(t), cs & 1, 0x61);
                 tc_fence_after();
@@ -664,10 +670,13 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full(t));
+                if (j == 0) PSTAMP(1);
             }
             // ---- item epilogue
+            PSTAMP(2);
             mbar_wait(pv_done(t), (cs - 1) & 1, 0x63);
             tc_fence_after();
+            PSTAMP(3);
             const int row = q0 + t * BQ + r;
             uint32_t o[32], o2[32];
             tmem_ld32(tm_o, o);
@@ -675,40 +684,55 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
             tmem_ld_wait();
             bool write_out = true;
             if (item.slot >= 0) {
-                // Split unit: publish this piece's un-normalised row (O, reference exponent, row sum); the piece that arrives last
-                // re-references all of them to the largest exponent, adds them up in piece order and writes the output.
+                // Split unit.  Pieces are numbered in key order and the persistent schedule hands them out so that piece 0 (the head) is
+                // always the LAST item of its CTA while every later piece is the FIRST (or only) item of a following CTA.  So a later
+                // piece publishes its un-normalised row (O, reference exponent, row sum, then -- behind a fence -- a per-row flag carrying this
+                // launch's generation number) and moves on at once; the head piece, which finishes last by construction, re-references
+                // all pieces to the largest exponent and adds them up in piece order (deterministic), its own row straight from TMEM.  No
+                // atomics, no CTA-wide handshake; the head's wait is bounded and in practice already satisfied.  Deadlock-free under any
+                // dispatch order: a waited-for piece depends on nothing.
                 const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
-                const int nthreads = two ? 256 : 128;
                 float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
-                float4* mine = reinterpret_cast<float4*>(unit_ws + ((size_t)piece * (NT * BQ) + t * BQ + r) * kWsRow);
+                if (piece != 0) {
+                    float4* mine = reinterpret_cast<float4*>(unit_ws + ((size_t)piece * (NT * BQ) + t * BQ + r) * kWsRow);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    mine[i / 4] = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
-                    mine[8 + i / 4] = make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3]));
-                }
-                mine[16] = make_float4(m_run, l_run, 0.f, 0.f);
-                __threadfence();
-                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-                if (warp == 2 && lane == 0) {
-                    const int arrived = atomicAdd(p.counters + item.slot, 1);
-                    if (arrived == n_pieces - 1) p.counters[item.slot] = 0;      // every piece has arrived: ready for the next launch
-                    *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) = arrived == n_pieces - 1;
-                }
-                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-                write_out = *reinterpret_cast<volatile int*>(smem + OFF_BAR + 208) != 0;
-                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");      // the flag is rewritten by this CTA's next split item
-                if (write_out) {
+                    for (int i = 0; i < 32; i += 4) {
+                        __stcg(mine + i / 4, make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3])));
+                        __stcg(mine + 8 + i / 4, make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3])));
+                    }
+                    __stcg(reinterpret_cast<float2*>(mine + 16), make_float2(m_run, l_run));
                     __threadfence();
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(mine + 16) + 2), "r"((uint32_t)p.gen) : "memory");
+                    write_out = false;
+                } else {
                     const float* rows = unit_ws + (size_t)(t * BQ + r) * kWsRow;
                     const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
-                    float m_all = -INFINITY;
-                    for (int q = 0; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
-                    l_run = 0.f;
+                    const long long t_spin = clock64();
+                    for (int q = 1; q < n_pieces; ++q) {                          // bounded wait for the row flags of the later pieces
+                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(rows + q * piece_stride + 66);
+                        uint32_t seen;
+                        uint32_t spins = 0;
+                        do {
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                            if (seen != (uint32_t)p.gen && (++spins & 0x3ff) == 0 && clock64() - t_spin > 8000000000ll) {
+                                atomicCAS(&g_dev_error, 0u, 0x71u | (blockIdx.x << 8));
+                                __threadfence_system();
+                                __trap();
+                            }
+                        } while (seen != (uint32_t)p.gen);
+                    }
+                    __threadfence();
+                    float m_all = m_run;
+                    for (int q = 1; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
+                    {
+                        const float w0 = ex2f(m_run - m_all);                      // own row first (piece order)
+                        l_run *= w0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { o[i] = 0u; o2[i] = 0u; }
-                    for (int q = 0; q < n_pieces; ++q) {
+                        for (int i = 0; i < 32; ++i) { o[i] = __float_as_uint(__uint_as_float(o[i]) * w0); o2[i] = __float_as_uint(__uint_as_float(o2[i]) * w0); }
+                    }
+                    for (int q = 1; q < n_pieces; ++q) {
                         const float4* src = reinterpret_cast<const float4*>(rows + q * piece_stride);
-                        const float4 ml = __ldcg(src + 16);
+                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(src + 16));
                         const float wq = ex2f(ml.x - m_all);
                         l_run = fmaf(ml.y, wq, l_run);
 #pragma unroll
@@ -726,6 +750,7 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                     }
                 }
             }
+            PSTAMP(4);
             const float inv_l = 1.0f / l_run;
             if (write_out && row < seg_end) {
                 uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
@@ -741,7 +766,9 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                                                 pack_half2(__uint_as_float(o2[i + 6]) * inv_l, __uint_as_float(o2[i + 7]) * inv_l));
                 }
             }
+            PSTAMP(5);
         }
+#undef PSTAMP
     }
     if (p.dbg && threadIdx.x == 64) {            // softmax warp 2, lane 0: [cta][4] = {start ns, end ns, cycles, SM id} (tools/fmha_cta_times.py)
         long long t1; unsigned smid;

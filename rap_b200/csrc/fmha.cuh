@@ -51,6 +51,8 @@ struct FmhaArgs {
     float* ws;           // partial rows [slot][piece][rows_per_cta][68] (64 un-normalised outputs, reference exponent, row sum, pad), or null
     int* counters;       // [n_slots] arrival counters, zero between launches (the combining CTA resets its counter)
     int ws_pieces;       // FmhaSchedule::max_pieces
+    int gen;             // persistent kernel: generation number of this launch (never 0, different from the previous launch on this workspace):
+                         // the value of the per-row "partial row published" flags inside the workspace
     long long* dbg;      // optional clock64() timeline of CTA 0: [iter][16] slots (tools/fmha_timeline.py), else null
 };
 
