@@ -406,7 +406,8 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
 //   * P.V(0) of item n+1 overwrites O (accumulate = 0): it waits for p_full, which the softmax warps only signal after their epilogue of
 //     item n has read O out of TMEM (program order in those warps), so no extra barrier is needed.
 // No CTA ever waits for another CTA: split units only publish partial rows, the piece that arrives last combines them.
-__global__ void __launch_bounds__(FCfg<2>::kThreads, 1)
+constexpr int kPersistThreads = FCfg<2>::kThreads + 32;     // + warp 10: publishes the "partial rows written" flag of a split unit's later piece
+__global__ void __launch_bounds__(kPersistThreads, 1)
 fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     using F = FCfg<2>;
     constexpr int NT = 2;
@@ -432,12 +433,15 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
     auto s_free = [&](int t) { return bar + 184 + 8 * t; };
     const uint32_t tmem_slot = bar + 200;
     const uint32_t q_empty = bar + 216;
+    auto part_ready = [&](int t) { return bar + 224 + 8 * t; };
 
     if (threadIdx.x == 0) {
         if (sbase & 1023u) { atomicCAS(&g_dev_error, 0u, 0xA1u); __trap(); }
         tma_prefetch_desc(&tm_qkv);
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
+        mbar_init(part_ready(0), 128);
+        mbar_init(part_ready(1), 128);
         for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
         mbar_fence_init();
@@ -536,6 +540,24 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                     ++cp[t];
                 }
                 s = s1; ph = ph1;
+            }
+        }
+    } else if (warp == 10) {
+        // ------------------------------------------------------------ publisher: a later piece (index >= 1) of a split unit is by construction the
+        // FIRST item of its CTA.  Its softmax threads store their partial rows and arrive on part_ready (cta-scope release); this warp then
+        // issues the gpu-scope fence (cumulative over what it synchronised with) and raises the piece's flag, so the fence latency is off the
+        // softmax warps' critical path.  The unit's head piece (last item of the preceding CTA) polls the flag.
+        if (it0 < it1) {
+            const FmhaItem item = p.items[it0];
+            if (item.slot >= 0 && (item.piece & 0xff) != 0) {
+                const bool two = item.q_row0 + BQ < item.seg_end;
+                mbar_wait(part_ready(0), 0, 0x72);
+                if (two) mbar_wait(part_ready(1), 0, 0x73);
+                __threadfence();
+                if (lane == 0) {
+                    float* flag = p.ws + ((size_t)item.slot * p.ws_pieces + (item.piece & 0xff)) * (NT * BQ) * kWsRow + 66;
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"((uint32_t)p.gen) : "memory");
+                }
             }
         }
     } else {
@@ -686,11 +708,11 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
             if (item.slot >= 0) {
                 // Split unit.  Pieces are numbered in key order and the persistent schedule hands them out so that piece 0 (the head) is
                 // always the LAST item of its CTA while every later piece is the FIRST (or only) item of a following CTA.  So a later
-                // piece publishes its un-normalised row (O, reference exponent, row sum, then -- behind a fence -- a per-row flag carrying this
-                // launch's generation number) and moves on at once; the head piece, which finishes last by construction, re-references
-                // all pieces to the largest exponent and adds them up in piece order (deterministic), its own row straight from TMEM.  No
-                // atomics, no CTA-wide handshake; the head's wait is bounded and in practice already satisfied.  Deadlock-free under any
-                // dispatch order: a waited-for piece depends on nothing.
+                // piece stores its un-normalised rows (O, reference exponent, row sum), hands the publication (gpu-scope fence + a flag
+                // carrying this launch's generation number) to warp 10 and moves on at once; the head piece, which finishes last by
+                // construction, re-references all pieces to the largest exponent and adds them up in piece order (deterministic), its own
+                // row straight from TMEM.  No atomics, no CTA-wide handshake; the head's wait is bounded and in practice already
+                // satisfied.  Deadlock-free under any dispatch order: a waited-for piece depends on nothing.
                 const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
                 float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
                 if (piece != 0) {
@@ -701,15 +723,14 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                         __stcg(mine + 8 + i / 4, make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3])));
                     }
                     __stcg(reinterpret_cast<float2*>(mine + 16), make_float2(m_run, l_run));
-                    __threadfence();
-                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(mine + 16) + 2), "r"((uint32_t)p.gen) : "memory");
+                    mbar_arrive(part_ready(t));                                    // warp 10 fences and raises the piece's flag
                     write_out = false;
                 } else {
                     const float* rows = unit_ws + (size_t)(t * BQ + r) * kWsRow;
                     const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
                     const long long t_spin = clock64();
                     for (int q = 1; q < n_pieces; ++q) {                          // bounded wait for the row flags of the later pieces
-                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(rows + q * piece_stride + 66);
+                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(unit_ws + q * piece_stride + 66);
                         uint32_t seen;
                         uint32_t spins = 0;
                         do {
@@ -1001,7 +1022,7 @@ int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaSt
             configured = true;
         }
         ProfScope _ps(KC_FMHA, st);
-        RAP_CUDA(launch_pdl(fmha_persist_kernel, dim3(n_ctas), dim3(FCfg<2>::kThreads), FCfg<2>::SMEM_BYTES, st, tm_qkv, a));
+        RAP_CUDA(launch_pdl(fmha_persist_kernel, dim3(n_ctas), dim3(kPersistThreads), FCfg<2>::SMEM_BYTES, st, tm_qkv, a));
         note_launch();
         return RAP_OK;
     }

@@ -255,6 +255,13 @@ def test_fmha_persistent_schedule_tiles_the_work_and_balances_the_ctas(cu, force
         if pieces[0][2] >= 0:
             slots.add(pieces[0][2])
     assert slots == set(range(n_slots))
+    # the kernel's combine protocol relies on this: a later piece (index >= 1) is the FIRST item of its CTA (it publishes and moves on), the head
+    # piece (index 0) of a cut unit is the LAST item of its CTA (it finishes last and combines) -- so a waited-for piece never waits itself
+    for a, b in zip(cta_ptr[:-1], cta_ptr[1:]):
+        for i in range(a, b):
+            slot, idx = items[i, 6], items[i, 7] & 0xff
+            if slot >= 0:
+                assert i == a if idx > 0 else i == b - 1
     blocks = (items[:, 5] - items[:, 4] + 127) // 128
     cost = blocks * np.where(items[:, 0] + 128 < items[:, 2], 1.0, 0.55) + 2.0
     per = np.array([cost[a:b].sum() for a, b in zip(cta_ptr[:-1], cta_ptr[1:])])
