@@ -343,8 +343,8 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
     for (auto& kv : d->entries)
         if (!kv.second.loaded) return fail(RAP_ESTATE, "rap_dit_finalize: missing key '%s'", kv.first.c_str());
     const int L = d->L;
-    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_x, d->w_emb_x, D, 64, 64, f32_bn()));
-    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_s, d->w_emb_s, D, 128, 128, f32_bn()));
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_x, d->w_emb_x, D, 64, 64, 128));       // B operands: 128-row boxes (a 256-wide tile = two boxes per stage,
+    RAP_TRY(make_tmap_f16_sw128(&d->tm_emb_s, d->w_emb_s, D, 128, 128, 128));    // or one per CTA of a multicast pair)
     RAP_TRY(make_tmap_f16_sw128(&d->tm_h0, d->wh0, D, D, D, 128));
     RAP_TRY(make_tmap_f16_sw128(&d->tm_h2, d->wh2, D / 2, D, D, 128));
     for (int b = 0; b < 2; ++b) { d->tm_qkv[b].resize(L); d->tm_out[b].resize(L); }
@@ -352,11 +352,11 @@ extern "C" int rap_dit_finalize(rap_dit_t* d) {
     for (int l = 0; l < L; ++l) {
         for (int b = 0; b < 2; ++b) {
             score_bound_kernel<<<1, 256>>>(d->gamma[b][l], d->score_bound + (size_t)(2 * l + b) * HEADS);
-            RAP_TRY(make_tmap_f16_sw128(&d->tm_qkv[b][l], d->wqkv[b][l], 3 * D, D, D, 256));
-            RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, f32_bn()));
+            RAP_TRY(make_tmap_f16_sw128(&d->tm_qkv[b][l], d->wqkv[b][l], 3 * D, D, D, 128));
+            RAP_TRY(make_tmap_f16_sw128(&d->tm_out[b][l], d->wout[b][l], D, D, D, 128));
         }
-        RAP_TRY(make_tmap_f16_sw128(&d->tm_w1[l], d->w1[l], 2 * FF_INNER, D, D, 256));
-        RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, f32_bn()));
+        RAP_TRY(make_tmap_f16_sw128(&d->tm_w1[l], d->w1[l], 2 * FF_INNER, D, D, 128));
+        RAP_TRY(make_tmap_f16_sw128(&d->tm_w2[l], d->w2[l], D, FF_INNER, FF_INNER, 128));
     }
     d->finalized = true;
     return RAP_OK;
@@ -713,7 +713,7 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
                              float* out32, void* out16, const float* gamma, void* dbg, void* stream) {
     CUtensorMap ta, tb;
     RAP_TRY(make_tmap_f16_sw128(&ta, A, M, K, K, 128));
-    RAP_TRY(make_tmap_f16_sw128(&tb, W, N, K, K, bn));
+    RAP_TRY(make_tmap_f16_sw128(&tb, W, N, K, K, 128));
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
     g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
@@ -726,7 +726,7 @@ extern "C" int rap_test_gemm_ln(int M, int K, const void* A, const void* W, cons
                                 const float* ln_add, const int32_t* row_of_tok, int row_stride, float one_plus, void* ln_out, void* stream) {
     CUtensorMap ta, tb;
     RAP_TRY(make_tmap_f16_sw128(&ta, A, M, K, K, 128));
-    RAP_TRY(make_tmap_f16_sw128(&tb, W, D, K, K, 256));
+    RAP_TRY(make_tmap_f16_sw128(&tb, W, D, K, K, 128));
     GemmArgs g{};
     g.M = M; g.N = D; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.ld32 = D;
     g.ln_mul = ln_mul; g.ln_add = ln_add; g.ln_row_of_tok = row_of_tok; g.ln_row_stride = row_stride; g.ln_one_plus = one_plus;

@@ -48,7 +48,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-template <int BN, int EPI>
+// MC (multicast): the kernel runs as 2-CTA clusters whose CTAs own vertically adjacent 128-row tiles of the SAME column tile.  Each CTA fetches
+// its own A tile and HALF of the shared B tile, multicast into both CTAs' stage (cp.async.bulk.tensor ... .multicast::cluster), so the weight
+// operand crosses the L2 -> SM fabric once per pair instead of once per CTA.  The K loops of these GEMMs are bound by exactly that traffic
+// ((128 + 256) rows x 128 B per 128x256x64 step at ~42 B/clk/SM of L2 bandwidth when every SM streams, against 512 tensor-pipe cycles), see
+// DESIGN.md.  A stage is free again when BOTH CTAs have consumed it: the empty barriers count two arrivals and every UMMA commit arrives on
+// the barrier of both CTAs (tcgen05.commit ... .multicast::cluster).
+template <int BN, int EPI, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
     using C = Cfg<BN>;
@@ -67,12 +73,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_blocks = p.K / BK;
-    const int num_tiles = m_tiles * n_tiles;
+    // Work units: tiles (one CTA each), or with MC pairs of vertically adjacent tiles (one cluster each; an odd last row of tiles gets a
+    // dummy partner whose loads are zero-filled and whose stores are masked).  first_tile / tile_step walk this CTA's units; unit -> (m0, n0).
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
+    const int num_tiles = MC ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+    const int first_tile = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m0 = [&](int tile) { return (MC ? 2 * (tile / n_tiles) + (int)crank : tile / n_tiles) * BM; };
+    auto tile_n0 = [&](int tile) { return (tile % n_tiles) * BN; };
+    constexpr int B_BOXES = BN / 128 > 0 ? BN / 128 : 1;      // the B tensor map has 128-row boxes (BN = 256: two per stage)
+    constexpr int B_BOX_ROWS = BN < 128 ? BN : 128;
+    constexpr int B_BOX_BYTES = B_BOX_ROWS * BK * 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
         mbar_fence_init();
     }
@@ -83,6 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if constexpr (MC) { cluster_arrive(); cluster_wait(); }     // the partner's barriers exist before anything is multicast at them
     const uint32_t tmem_base = *tmem_slot_gen;
     // Programmatic dependent launch: only the A operand, the residual and the outputs depend on the previous kernel.  The weight
     // (B) tiles of the first pipeline stages are requested BEFORE griddepcontrol.wait, so their fetch latency hides under the
@@ -95,18 +111,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------ TMA producer (warp converged, one elected lane issues)
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
-        const int pre = (blockIdx.x < num_tiles) ? min(C::STAGES, k_blocks) : 0;   // stages whose B tile is in flight before the wait
+        const int pre = (first_tile < num_tiles) ? min(C::STAGES, k_blocks) : 0;   // stages whose B tile is in flight before the wait
+        auto load_b = [&](uint32_t sb, uint32_t bar, int kcol, int n0) {            // this CTA's share of the B tile of one stage
+            if constexpr (MC) {
+                tma_load_2d_mc(sb + crank * B_BOX_BYTES, &tmB, bar, kcol, n0 + (int)crank * B_BOX_ROWS, (uint16_t)3);
+            } else {
+#pragma unroll
+                for (int h = 0; h < B_BOXES; ++h) tma_load_2d(sb + h * B_BOX_BYTES, &tmB, bar, kcol, n0 + h * B_BOX_ROWS);
+            }
+        };
         if (leader) {
-            const int n0 = (blockIdx.x % n_tiles) * BN;
+            const int n0 = tile_n0(first_tile);
             for (int kb = 0; kb < pre; ++kb) {
                 mbar_expect_tx(full_bar(kb), C::STAGE_BYTES);
-                tma_load_2d(smem_base + kb * C::STAGE_BYTES + A_STAGE_BYTES, &tmB, full_bar(kb), kb * BK, n0);
+                load_b(smem_base + kb * C::STAGE_BYTES + A_STAGE_BYTES, full_bar(kb), kb * BK, n0);
             }
         }
         pdl_wait();
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            const bool first = tile == (int)blockIdx.x;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {
+            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+            const bool first = tile == first_tile;
             GEMM_TS(0);
             for (int kb = 0; kb < k_blocks; ++kb) {
                 const bool b_done = first && kb < pre;          // this stage's barrier is armed and its B tile already requested
@@ -121,7 +145,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         a_row = m0 + (tap / 3 - 1) * p.conv_pitch + (tap % 3 - 1);
                     }
                     tma_load_2d(sa, &tmA, full_bar(stage), a_col, a_row);
-                    if (!b_done) tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+                    if (!b_done) load_b(sa + A_STAGE_BYTES, full_bar(stage), kb * BK, n0);
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -133,7 +157,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool leader = elect_one();
         constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {
             GEMM_TS(2);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1, 0x21);
             tc_fence_after();
@@ -148,7 +172,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)   // +32 bytes (encoded +2) per K=16 step inside the swizzle row
                         umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(empty_bar(stage));       // frees the smem stage when these MMAs retire
+                    if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)3);   // both CTAs of the pair learn that this one is done with the stage
+                    else umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -178,8 +203,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         const bool dbg_w = warp == 2;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++dbg_tile) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {
+            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             if (dbg_w) GEMM_TS(5);
             const int row_base = m0 + q * 32;            // first of this warp's 32 rows
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
@@ -446,31 +471,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC) { cluster_arrive(); cluster_wait(); }     // no CTA leaves while its partner may still multicast into it / arrive on its barriers
     if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool MC = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = ceil_div(a.M, BM) * (a.N / BN);
-    const int grid = (EPI == EPI_F32_LN || tiles < num_sms()) ? tiles : num_sms();
+    const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN;
     ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
+    if constexpr (MC) {
+        const int pairs = ((m_tiles + 1) / 2) * n_tiles;
+        const int clusters = std::min(pairs, num_sms() / 2);
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, true>, dim3(2 * clusters), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        note_launch();
+        return RAP_OK;
+    }
+    const int tiles = m_tiles * n_tiles;
+    const int grid = (EPI == EPI_F32_LN || tiles < num_sms()) ? tiles : num_sms();
     if constexpr (EPI == EPI_F32_LN) {
         // one 128x256 tile per CTA, the two CTAs of a 128-row block (column halves) are a cluster: CTA rank = blockIdx.x & 1 = N-tile index
         RAP_REQUIRE(a.N == 2 * BN && a.ln_out && a.ln_mul && a.ln_add && a.ln_row_of_tok && !a.table && !a.out16 && !a.conv_pitch,
                     "gemm: the LayerNorm epilogue needs N = 512 and the ln_* arguments (no table / fp16 shadow / convolution)");
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
         note_launch();
         return RAP_OK;
     }
-    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, tmA, tmB, a));
+    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, tmA, tmB, a));
     note_launch();
     return RAP_OK;
+}
+
+// RAP_GEMM_MC=0: every CTA fetches its own B tile (A/B measurements); default: 2-CTA clusters share the B tile by multicast.
+bool gemm_multicast() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_GEMM_MC"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
 }
 
 }  // namespace
@@ -478,10 +519,11 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
 int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
     RAP_REQUIRE(a.M > 0 && a.N % BN == 0 && a.K % BK == 0 && a.K >= BK, "gemm: bad shape M=%d N=%d K=%d BN=%d", a.M, a.N, a.K, BN);
     if (BN == 256) {
+        const bool mc = gemm_multicast() && !a.conv_pitch && a.M > BM;      // a single row of tiles has nothing to share
         switch (epi) {
-            case EPI_F32: return launch_t<256, EPI_F32>(tmA, tmB, a, st);
-            case EPI_QKV: return launch_t<256, EPI_QKV>(tmA, tmB, a, st);
-            case EPI_GEGLU: return launch_t<256, EPI_GEGLU>(tmA, tmB, a, st);
+            case EPI_F32: return mc ? launch_t<256, EPI_F32, true>(tmA, tmB, a, st) : launch_t<256, EPI_F32>(tmA, tmB, a, st);
+            case EPI_QKV: return mc ? launch_t<256, EPI_QKV, true>(tmA, tmB, a, st) : launch_t<256, EPI_QKV>(tmA, tmB, a, st);
+            case EPI_GEGLU: return mc ? launch_t<256, EPI_GEGLU, true>(tmA, tmB, a, st) : launch_t<256, EPI_GEGLU>(tmA, tmB, a, st);
             case EPI_F32_LN: return launch_t<256, EPI_F32_LN>(tmA, tmB, a, st);
             default: break;
         }

@@ -101,6 +101,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
         ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// Same, multicast: the box lands at the same shared-memory offset of every CTA of the cluster named in cta_mask, and each destination CTA's
+// mbarrier at that offset receives the complete_tx for the bytes written into ITS shared memory.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {   // one full warp
@@ -151,6 +159,12 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // Arrive on an mbarrier when all previously issued UMMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Same, arriving on the mbarrier at this offset in every CTA of the cluster named in cta_mask (a stage fed by multicast is free only when
+// every CTA that received it has consumed it).
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // TMEM -> registers: warp w reads lanes [32*(w%4), +32); thread = one lane (row), 32 consecutive columns.
