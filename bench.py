@@ -278,6 +278,7 @@ def extra_configs(dev, sd) -> dict:
     from rap_b200.synth import make_batch
     out = {}
     for key, (label, B, V, N, S, rigid, reps) in {
+            "cfg1": ("configs[0]: 1 pair, 2 x 512 pts, 5 steps (launch-bound size: 690 kernels of a few microseconds)", 1, 2, 512, 5, False, 20),
             "cfg3": ("configs[2]: 1 scene, 4 views x 4096 pts, 20 steps, rigidity forcing on", 1, 4, 4096, 20, True, 2),
             "cfg4_share": ("configs[3] share of one GPU: 32 pairs x 2 x 4096 pts, 20 steps", 32, 2, 4096, 20, False, 1),
             "cfg5_share": ("configs[4] shape: 2 of one GPU's 8 pairs x 2 x 16384 pts, 50 steps", 2, 2, 16384, 50, False, 1)}.items():
