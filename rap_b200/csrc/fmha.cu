@@ -769,6 +769,11 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                             o2[i + 3] = __float_as_uint(fmaf(b.w, wq, __uint_as_float(o2[i + 3])));
                         }
                     }
+                    // Consumed: clear the flags (this CTA is their only reader), so a workspace never carries a flag into a later launch -- the
+                    // generation number is then a second line of defence only (e.g. replays of a captured launch reuse their numbers).
+                    asm volatile("bar.sync 2, %0;" ::"r"(two ? 256 : 128) : "memory");
+                    if (warp == 2 && lane == 0)
+                        for (int q = 1; q < n_pieces; ++q) *reinterpret_cast<volatile uint32_t*>(unit_ws + q * piece_stride + 66) = 0u;
                 }
             }
             PSTAMP(4);
