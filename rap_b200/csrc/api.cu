@@ -368,7 +368,16 @@ struct rap_plan {
     int T = 0, B = 0, P = 0, VP = 0, n_cap = 0;
     int n_items_part = 0, n_items_batch = 0, fmha_pieces_part = 0, fmha_pieces_batch = 0;   // n_items_*: grid of the launch (CTAs)
     int *cta_ptr_part = nullptr, *cta_ptr_batch = nullptr;
-    int fmha_gen = 0;              // generation number of the last attention launch on this plan's workspace (FmhaArgs::gen)   // persistent attention schedule: item range of every CTA (null: one item per CTA)
+    int fmha_gen = 0;              // generation number of the last attention launch on this plan's workspace (FmhaArgs::gen)
+    // Whole-sampler CUDA graph (small scenes are launch-bound: 137 kernels of a few microseconds per flow step).  The graph works on plan-owned
+    // staging buffers, so the caller's pointers never enter it; it is captured on a private stream and launched into the caller's.
+    struct SamplerGraph { int steps = 0, rigid = 0, outs = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::vector<SamplerGraph> graphs;
+    int eager_calls = 0;           // the first sampler call runs eagerly (function attributes, lazy module loading), the second one captures
+    bool graphs_failed = false;
+    cudaStream_t gstream = nullptr;
+    float *g_x1 = nullptr, *g_ep = nullptr, *g_tr = nullptr, *g_xf = nullptr, *g_feat = nullptr, *cond_copy = nullptr;
+    int g_steps_cap = 0;   // persistent attention schedule: item range of every CTA (null: one item per CTA)
     char* ws = nullptr;
     // layout
     int *cu_part = nullptr, *slot = nullptr, *scene_of_tok = nullptr, *zero_rows = nullptr;
@@ -477,6 +486,9 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
 
 extern "C" void rap_plan_destroy(rap_plan_t* pl) {
     if (!pl) return;
+    for (auto& g : pl->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (pl->gstream) cudaStreamDestroy(pl->gstream);
+    for (float* p : {pl->g_x1, pl->g_ep, pl->g_tr, pl->g_xf, pl->g_feat, pl->cond_copy}) cudaFree(p);
     cudaFree(pl->ws);
     delete pl;
 }
@@ -491,7 +503,9 @@ extern "C" int rap_plan_set_condition(rap_plan_t* pl, const float* cond, const f
     GemmArgs g{};
     g.M = pl->T; g.N = D; g.K = 128; g.bias = d->b_emb; g.out32 = pl->h_static; g.ld32 = D; g.table = d->anchor_emb; g.sel = anchor;
     RAP_TRY(launch_gemm(EPI_F32, f32_bn(), pl->tm_as, d->tm_emb_s, g, st));
-    pl->cond = cond; pl->anchor = anchor; pl->condition_set = true;
+    if (!pl->cond_copy) RAP_CUDA(cudaMalloc(&pl->cond_copy, sizeof(float) * 3 * (size_t)pl->T));
+    RAP_CUDA(cudaMemcpyAsync(pl->cond_copy, cond, sizeof(float) * 3 * (size_t)pl->T, cudaMemcpyDeviceToDevice, st));
+    pl->cond = pl->cond_copy; pl->anchor = anchor; pl->condition_set = true;
     return RAP_OK;
 }
 
@@ -642,14 +656,12 @@ extern "C" int rap_dit_forward(rap_plan_t* pl, const float* x, const float* time
     return RAP_OK;
 }
 
-extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps, int rigidity_forcing, float* end_traj, float* traj,
-                                float* x_final, float* features, void* stream) {
-    RAP_REQUIRE(pl && x_1, "rap_sample_euler: NULL argument");
-    RAP_REQUIRE(pl->condition_set, "rap_sample_euler: call rap_plan_set_condition first");
-    RAP_REQUIRE(num_steps >= 1 && num_steps <= pl->n_cap, "rap_sample_euler: num_steps=%d outside [1,%d] (max_timesteps of the plan)", num_steps, pl->n_cap);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace {
+
+// Enqueues the whole S-step sampler on `st` (kernels + device-to-device copies only, no host synchronisation).
+int enqueue_sampler(rap_plan* pl, const float* x_1, int num_steps, int rigidity_forcing, float* end_traj, float* traj, float* x_final, float* features,
+                    cudaStream_t st) {
     const size_t row = (size_t)pl->T * 3;
-    pin_residual_stream(pl, st);
     sampler_timesteps_kernel<<<ceil_div(num_steps, 64), 64, 0, st>>>(pl->tbuf, num_steps);
     RAP_CUDA(cudaGetLastError());
     note_launch(1);
@@ -665,12 +677,102 @@ extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps,
         if (rigidity_forcing) {
             // x_t = rigid(x0_hat) * (1 - t + dt) + x_1 * (t - dt)      (sampler.py:59-60)
             RAP_TRY(launch_procrustes(pl->cond, x0hat, pl->cu_part, nullptr, pl->VP, nullptr, nullptr, pl->x_t, traj ? traj + step * row : nullptr,
-                                      x_1, (float)(1.0 - t + dt), (float)(t - dt), st));
+                                      x_1, (float)(1.0 - t + dt), (float)(t - dt), st, nullptr, nullptr, nullptr, pl->T));
         }
     }
     if (x_final) RAP_CUDA(cudaMemcpyAsync(x_final, pl->x_t, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));
     if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->h, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
-    unpin_residual_stream(st);
+    return RAP_OK;
+}
+
+// RAP_GRAPH: 1 = always replay the sampler as a CUDA graph, 0 = never, unset = for batches of at most kGraphTokens tokens (where the ~2.5 us
+// a stream launch costs the host is comparable to a kernel's run time; at cfg2 sizes the kernels are 10-100x longer and nothing is gained).
+constexpr int kGraphTokens = 3072;
+int graph_mode() {                                            // read per call (one getenv per sampler call): tests flip it inside one process
+    const char* e = getenv("RAP_GRAPH");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+}
+
+int ensure_graph_buffers(rap_plan* pl, int num_steps) {
+    const size_t row = (size_t)pl->T * 3;
+    if (!pl->gstream) RAP_CUDA(cudaStreamCreateWithFlags(&pl->gstream, cudaStreamNonBlocking));
+    if (!pl->g_x1) {
+        RAP_CUDA(cudaMalloc(&pl->g_x1, sizeof(float) * row));
+        RAP_CUDA(cudaMalloc(&pl->g_xf, sizeof(float) * row));
+        RAP_CUDA(cudaMalloc(&pl->g_feat, sizeof(float) * (size_t)pl->T * D));
+    }
+    if (num_steps > pl->g_steps_cap) {           // trajectories grow with the step count: re-allocate and drop the graphs that point at the old ones
+        for (auto& g : pl->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        pl->graphs.clear();
+        cudaFree(pl->g_ep); cudaFree(pl->g_tr);
+        pl->g_ep = pl->g_tr = nullptr;
+        RAP_CUDA(cudaMalloc(&pl->g_ep, sizeof(float) * row * num_steps));
+        RAP_CUDA(cudaMalloc(&pl->g_tr, sizeof(float) * row * num_steps));
+        pl->g_steps_cap = num_steps;
+    }
+    return RAP_OK;
+}
+
+}  // namespace
+
+extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps, int rigidity_forcing, float* end_traj, float* traj,
+                                float* x_final, float* features, void* stream) {
+    RAP_REQUIRE(pl && x_1, "rap_sample_euler: NULL argument");
+    RAP_REQUIRE(pl->condition_set, "rap_sample_euler: call rap_plan_set_condition first");
+    RAP_REQUIRE(num_steps >= 1 && num_steps <= pl->n_cap, "rap_sample_euler: num_steps=%d outside [1,%d] (max_timesteps of the plan)", num_steps, pl->n_cap);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t row = (size_t)pl->T * 3;
+    const int mode = graph_mode();
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
+    const bool want_graph = !pl->graphs_failed && !profiling_enabled() && capturing == cudaStreamCaptureStatusNone &&    // (a caller capturing us gets plain launches)
+                            (mode == 1 || (mode == -1 && pl->T <= kGraphTokens));
+    if (!want_graph || pl->eager_calls++ == 0) {
+        pin_residual_stream(pl, st);
+        const int rc = enqueue_sampler(pl, x_1, num_steps, rigidity_forcing, end_traj, traj, x_final, features, st);
+        unpin_residual_stream(st);
+        return rc;
+    }
+    // ---- graph route: inputs -> staging, replay (capturing first if this (steps, rigidity, outputs) combination is new), staging -> outputs
+    RAP_TRY(ensure_graph_buffers(pl, num_steps));
+    const int outs = (end_traj ? 1 : 0) | (traj ? 2 : 0) | (x_final ? 4 : 0) | (features ? 8 : 0);
+    rap_plan::SamplerGraph* g = nullptr;
+    for (auto& c : pl->graphs) if (c.steps == num_steps && c.rigid == (rigidity_forcing ? 1 : 0) && c.outs == outs) g = &c;
+    if (!g) {
+        cudaGraph_t graph = nullptr;
+        const int64_t before = rap_launch_count();
+        pin_residual_stream(pl, pl->gstream);                 // kernel nodes inherit the capturing stream's access-policy window
+        cudaError_t e = cudaStreamBeginCapture(pl->gstream, cudaStreamCaptureModeRelaxed);
+        int rc = e == cudaSuccess ? enqueue_sampler(pl, pl->g_x1, num_steps, rigidity_forcing, end_traj ? pl->g_ep : nullptr, traj ? pl->g_tr : nullptr,
+                                                    x_final ? pl->g_xf : nullptr, features ? pl->g_feat : nullptr, pl->gstream)
+                                  : RAP_ECUDA;
+        if (e == cudaSuccess) e = cudaStreamEndCapture(pl->gstream, &graph);
+        unpin_residual_stream(pl->gstream);
+        cudaGraphExec_t exec = nullptr;
+        if (e == cudaSuccess && rc == RAP_OK && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess || rc != RAP_OK || !exec) {      // capture is an optimisation: fall back to stream launches for good
+            cudaGetLastError();
+            pl->graphs_failed = true;
+            note_launch((int)(before - rap_launch_count()));
+            pin_residual_stream(pl, st);
+            rc = enqueue_sampler(pl, x_1, num_steps, rigidity_forcing, end_traj, traj, x_final, features, st);
+            unpin_residual_stream(st);
+            return rc;
+        }
+        rap_plan::SamplerGraph ng;
+        ng.steps = num_steps; ng.rigid = rigidity_forcing ? 1 : 0; ng.outs = outs; ng.exec = exec; ng.launches = rap_launch_count() - before;
+        note_launch((int)-ng.launches);                       // counted when the graph actually runs (below)
+        pl->graphs.push_back(ng);
+        g = &pl->graphs.back();
+    }
+    RAP_CUDA(cudaMemcpyAsync(pl->g_x1, x_1, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));
+    RAP_CUDA(cudaGraphLaunch(g->exec, st));
+    note_launch((int)g->launches);
+    if (end_traj) RAP_CUDA(cudaMemcpyAsync(end_traj, pl->g_ep, sizeof(float) * row * num_steps, cudaMemcpyDeviceToDevice, st));
+    if (traj) RAP_CUDA(cudaMemcpyAsync(traj, pl->g_tr, sizeof(float) * row * num_steps, cudaMemcpyDeviceToDevice, st));
+    if (x_final) RAP_CUDA(cudaMemcpyAsync(x_final, pl->g_xf, sizeof(float) * row, cudaMemcpyDeviceToDevice, st));
+    if (features) RAP_CUDA(cudaMemcpyAsync(features, pl->g_feat, sizeof(float) * (size_t)pl->T * D, cudaMemcpyDeviceToDevice, st));
     return RAP_OK;
 }
 
@@ -716,6 +818,8 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     RAP_TRY(make_tmap_f16_sw128(&tb, W, N, K, K, 128));
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
+    g.mc = (epi >> 8) & 3;                                       // test hook: epi | 0x100 forces the multicast variant, | 0x200 forbids it
+    epi &= 0xff;
     g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
 }

@@ -734,7 +734,7 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                         uint32_t seen;
                         uint32_t spins = 0;
                         do {
-                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");   // pairs with warp 10's fence + store
                             if (seen != (uint32_t)p.gen && (++spins & 0x3ff) == 0 && clock64() - t_spin > 8000000000ll) {
                                 atomicCAS(&g_dev_error, 0u, 0x71u | (blockIdx.x << 8));
                                 __threadfence_system();
@@ -742,7 +742,6 @@ fmha_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p
                             }
                         } while (seen != (uint32_t)p.gen);
                     }
-                    __threadfence();
                     float m_all = m_run;
                     for (int q = 1; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
                     {

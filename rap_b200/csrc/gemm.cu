@@ -507,10 +507,13 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
     return RAP_OK;
 }
 
-// RAP_GEMM_MC=0: every CTA fetches its own B tile (A/B measurements); default: 2-CTA clusters share the B tile by multicast.
+// RAP_GEMM_MC=1: 2-CTA clusters share the B tile by multicast.  Built, parity-tested and measured (r02, same-box alternating A/B, 3 rounds):
+// 99.59 / 99.66 / 99.50 ms per pair with it, 99.46 / 99.56 / 99.54 without; in isolation 2-10 % SLOWER (QKV 16.6 vs 15.9 us, out-proj 10.3 vs
+// 9.4).  It removes 27 % of the L2 reads (ncu lts__throughput 37.9 % -> 27.6 % on the GEGLU GEMM) but not one byte of what each SM has to
+// ingest, which is what bounds the K loop, and it couples the two CTAs' pipelines.  Hence off by default.
 bool gemm_multicast() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("RAP_GEMM_MC"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    if (v < 0) { const char* e = getenv("RAP_GEMM_MC"); v = (e && atoi(e) == 1) ? 1 : 0; }
     return v == 1;
 }
 
@@ -519,7 +522,7 @@ bool gemm_multicast() {
 int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
     RAP_REQUIRE(a.M > 0 && a.N % BN == 0 && a.K % BK == 0 && a.K >= BK, "gemm: bad shape M=%d N=%d K=%d BN=%d", a.M, a.N, a.K, BN);
     if (BN == 256) {
-        const bool mc = gemm_multicast() && !a.conv_pitch && a.M > BM;      // a single row of tiles has nothing to share
+        const bool mc = (a.mc == 1 || (a.mc == 0 && gemm_multicast())) && !a.conv_pitch && a.M > BM;      // a single row of tiles has nothing to share
         switch (epi) {
             case EPI_F32: return mc ? launch_t<256, EPI_F32, true>(tmA, tmB, a, st) : launch_t<256, EPI_F32>(tmA, tmB, a, st);
             case EPI_QKV: return mc ? launch_t<256, EPI_QKV, true>(tmA, tmB, a, st) : launch_t<256, EPI_QKV>(tmA, tmB, a, st);

@@ -26,8 +26,8 @@ def _sync_check(rap):
 def _gemm(rap, epi, bn, A, W, bias=None, addend=None, gamma=None, out16_cols=None):
     M, K = A.shape
     N = W.shape[0]
-    out32 = torch.zeros(M, N, device="cuda") if epi == 0 else None
-    out16 = torch.zeros(M, out16_cols or N, device="cuda", dtype=torch.float16) if (epi != 0 or out16_cols) else None
+    out32 = torch.zeros(M, N, device="cuda") if (epi & 0xff) == 0 else None
+    out16 = torch.zeros(M, out16_cols or N, device="cuda", dtype=torch.float16) if ((epi & 0xff) != 0 or out16_cols) else None
     rap.check(rap.lib.rap_test_gemm(epi, bn, M, N, K, A.data_ptr(), W.data_ptr(), rap.ptr(bias), rap.ptr(addend), rap.ptr(out32),
                                     rap.ptr(out16), rap.ptr(gamma), None, rap.stream_ptr()), "rap_test_gemm")
     _sync_check(rap)
@@ -75,6 +75,24 @@ def test_gemm_f32_layernorm_epilogue(rap, M, K, in_place, per_row):
     ln_ref = F.layer_norm(ref, (512,)) * (one_plus + mul[rows.long()]) + add[rows.long()]
     err = (ln_out.float() - ln_ref).abs().max().item()
     assert err < 2e-2, f"max err {err}"
+
+
+@pytest.mark.parametrize("M", [8192, 257, 1000])
+def test_gemm_multicast_cluster_variant(rap, M):
+    """The opt-in 2-CTA-cluster GEMM (weight tile fetched half by each CTA and multicast into both, two-arrival stage barriers):
+    f32 residual, QKV + RMS-norm and GEGLU epilogues, even and odd numbers of 128-row tiles (257 -> a dummy partner tile)."""
+    g = torch.Generator("cuda").manual_seed(M)
+    A = torch.randn(M, 512, device="cuda", generator=g).half()
+    W = (torch.randn(512, 512, device="cuda", generator=g) / 22.6).half()
+    bias, add = torch.randn(512, device="cuda", generator=g), torch.randn(M, 512, device="cuda", generator=g)
+    out32, _ = _gemm(rap, 0 | 0x100, 256, A, W, bias, add)
+    assert (out32 - (A.float() @ W.float().t() + bias + add)).abs().max().item() < 2e-3
+    Wq = (torch.randn(1536, 512, device="cuda", generator=g) / 22).half()
+    gamma = 1 + 0.1 * torch.randn(2, 8, 64, device="cuda", generator=g)
+    _, out16 = _gemm(rap, 2 | 0x100, 256, A, Wq, gamma=gamma)
+    qkv = (A.float() @ Wq.float().t()).view(M, 3, 8, 64)
+    ref = torch.stack([F.normalize(qkv[:, 0], dim=-1) * gamma[0] * 8, F.normalize(qkv[:, 1], dim=-1) * gamma[1] * 8, qkv[:, 2]], 1).reshape(M, 1536)
+    assert (out16.float() - ref).abs().max().item() < 2e-2
 
 
 def test_gemm_silu_f16(rap):
