@@ -685,9 +685,13 @@ int enqueue_sampler(rap_plan* pl, const float* x_1, int num_steps, int rigidity_
     return RAP_OK;
 }
 
-// RAP_GRAPH: 1 = always replay the sampler as a CUDA graph, 0 = never, unset = for batches of at most kGraphTokens tokens (where the ~2.5 us
-// a stream launch costs the host is comparable to a kernel's run time; at cfg2 sizes the kernels are 10-100x longer and nothing is gained).
-constexpr int kGraphTokens = 3072;
+// RAP_GRAPH: 1 = always replay the sampler as a CUDA graph, 0 = never, unset = whenever the trajectory staging buffers stay below
+// kGraphStagingBytes.  Measured (tools/graph_ab.py, one B200): 6.32 -> 6.22 ms at 2 x 512 points / 5 steps, 29.83 -> 29.47 ms at 2 x 1024 / 20
+// steps, 99.17 -> 98.39 ms at 2 x 4096 / 20 steps: 1-2 % everywhere -- the path is not launch-bound even at 1024 tokens (690 kernels in 6.3 ms:
+// the kernels' own fixed latencies, ~9 us each, are the floor there), the graph only removes the host-side launch gaps.
+// A plan captures on its THIRD sampler call: layouts that are used once or twice (dynamic batch samplers) never pay for an instantiation.
+constexpr size_t kGraphStagingBytes = (size_t)256 << 20;
+constexpr int kEagerCallsBeforeCapture = 2;
 int graph_mode() {                                            // read per call (one getenv per sampler call): tests flip it inside one process
     const char* e = getenv("RAP_GRAPH");
     return e ? (atoi(e) != 0 ? 1 : 0) : -1;
@@ -726,8 +730,8 @@ extern "C" int rap_sample_euler(rap_plan_t* pl, const float* x_1, int num_steps,
     cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &capturing) != cudaSuccess) { cudaGetLastError(); capturing = cudaStreamCaptureStatusNone; }
     const bool want_graph = !pl->graphs_failed && !profiling_enabled() && capturing == cudaStreamCaptureStatusNone &&    // (a caller capturing us gets plain launches)
-                            (mode == 1 || (mode == -1 && pl->T <= kGraphTokens));
-    if (!want_graph || pl->eager_calls++ == 0) {
+                            (mode == 1 || (mode == -1 && 2 * sizeof(float) * row * (size_t)num_steps <= kGraphStagingBytes));
+    if (!want_graph || pl->eager_calls++ < kEagerCallsBeforeCapture) {
         pin_residual_stream(pl, st);
         const int rc = enqueue_sampler(pl, x_1, num_steps, rigidity_forcing, end_traj, traj, x_final, features, st);
         unpin_residual_stream(st);

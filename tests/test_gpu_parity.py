@@ -271,9 +271,9 @@ def test_procrustes_part_table_past_the_cloud_is_refused_on_the_device():
 
 @pytest.mark.parametrize("name,force", [("cfg1_2x512_s5_rigid", None), ("ragged_b2_v3_L2_s3_rigid", None), ("cfg1_2x512_s5", "1")])
 def test_sampler_cuda_graph_replays_equal_stream_launches(golden_dir, name, force, monkeypatch):
-    """Small batches (<= 3072 tokens; or RAP_GRAPH=1) replay the whole sampler as one CUDA graph on plan-owned staging buffers: the first
-    call of a plan runs as stream launches, the second captures, later ones replay -- all must give the same trajectories (the kernels
-    are deterministic), also after the condition changed and with freshly allocated output tensors every call."""
+    """The whole sampler replays as one CUDA graph on plan-owned staging buffers: the first two calls of a plan run as stream launches, the
+    third captures, later ones replay -- all must give the same trajectories (the kernels are deterministic), also after the condition
+    changed and with freshly allocated output tensors every call."""
     from rap_b200 import _lib
     from rap_b200.engine import DiTHandle, Plan
     if force is not None:
@@ -287,16 +287,16 @@ def test_sampler_cuda_graph_replays_equal_stream_launches(golden_dir, name, forc
     plan.set_condition(b.cond, b.features, b.scales, b.anchor_indices)
     n0 = _lib.lib.rap_launch_count()
     outs = []
-    for i in range(4):
+    for i in range(6):
         outs.append(plan.sample(b.x_1, S, rigid, return_trajectory=True, return_features=(i % 2 == 0)))
         _check_clean()
-    per_call = (_lib.lib.rap_launch_count() - n0) // 4
+    per_call = (_lib.lib.rap_launch_count() - n0) // 6
     assert per_call >= 11 * L * S                                   # replays are counted like the launches they contain
     for o in outs[1:]:
         assert torch.equal(o["end_point_trajectory"], outs[0]["end_point_trajectory"]) and torch.equal(o["trajectory"], outs[0]["trajectory"])
         assert torch.equal(o["x_final"], outs[0]["x_final"])
-    assert torch.equal(outs[2]["transformer_features"], outs[0]["transformer_features"])
-    mx, mean = _stats(outs[3]["end_point_trajectory"], g["end_point_trajectory"])
+    assert torch.equal(outs[4]["transformer_features"], outs[0]["transformer_features"])
+    mx, mean = _stats(outs[5]["end_point_trajectory"], g["end_point_trajectory"])
     assert mean <= SMP_MEAN_CAP
     # a different condition on the same plan (same layout): the graph reads plan-owned buffers, so the replay must follow it
     other = make_batch(B, V, N, max_parts=V + 2, first_scene=7).to("cuda")
