@@ -955,43 +955,68 @@ FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int head
         }
         return sch;
     }
+    // Whole waves first: unit k * G + c goes to CTA c, so that at any moment all CTAs work inside the same window of ~G consecutive units
+    // (a handful of (segment, head) K/V streams -> L2-resident; contiguous per-CTA ranges of a large batch would spread the CTAs over every
+    // (scene, head) stream at once -- 128 MB of K/V at 8 pairs -- and thrash L2).  Only the LAST, partial wave is cut stream-K style, each
+    // CTA receiving what it is short of the common target.
+    const size_t U = units.size();
+    const size_t n_whole = (U / (size_t)G) * (size_t)G;
+    std::vector<double> load((size_t)G, 0.0);
+    for (size_t ui = 0; ui < n_whole; ++ui) load[ui % (size_t)G] += units[ui].blocks * units[ui].w + kItemOverhead;
+    double rem_work = 0.0;
+    for (size_t ui = n_whole; ui < U; ++ui) rem_work += units[ui].blocks * units[ui].w;
+    double load_sum = 0.0;
+    for (double l : load) load_sum += l;
+    n_items = (U - n_whole) + (size_t)G;
     for (int pass = 0; pass < 8; ++pass) {                                   // the item count feeds back into the target: keep the best pass
-        // CTA c ends where the running cost reaches (c + 1) * target: rounding to whole blocks does not accumulate towards the last CTA
-        const double target = std::max((work + kItemOverhead * (double)n_items) / G, floor_target);
-        per_cta.assign(1, {});
+        // capacity of CTA c = target - load[c] (what it is short of); CTA c's share of the remainder ends where the running cost reaches the
+        // running capacity: rounding to whole blocks does not accumulate towards the last CTA
+        double target = std::max((load_sum + rem_work + kItemOverhead * (double)n_items) / G, floor_target);
+        for (int it = 0; it < 4; ++it) {                                     // CTAs already above the target take nothing: re-level the others
+            double cap = 0.0;
+            int open = 0;
+            for (double l : load) if (l < target) { cap += target - l; ++open; }
+            const double need = rem_work + kItemOverhead * (double)n_items;
+            if (open == 0 || std::abs(cap - need) < 1e-6 * (need + 1.0)) break;
+            target += (need - cap) / open;
+        }
+        std::vector<double> cum((size_t)G, 0.0);
+        double run = 0.0;
+        for (int c = 0; c < G; ++c) { run += std::max(0.0, target - load[c]); cum[c] = run; }
+        per_cta.assign((size_t)G, {});
         pieces_of_unit.assign(units.size(), 0);
         double assigned = 0.0;
-        for (size_t ui = 0; ui < units.size(); ++ui) {
+        int c = 0;
+        for (size_t ui = n_whole; ui < U; ++ui) {
             const Unit& u = units[ui];
             int b = 0;
             while (b < u.blocks) {
-                const bool last_cta = (int)per_cta.size() >= G;
-                const double budget = last_cta ? 1e30 : (double)per_cta.size() * target - assigned;
+                const bool last_cta = c >= G - 1;
+                const double budget = last_cta ? 1e30 : cum[c] - assigned;
                 const int left = u.blocks - b;
                 int take = left;
                 if (left * u.w + kItemOverhead > budget + 0.5 * u.w) {
                     take = (int)((budget - kItemOverhead) / u.w + 0.5);
                     if (take > left - kMinPieceBlocks) take = left - kMinPieceBlocks;   // never leave a sliver behind ...
                     if (take < kMinPieceBlocks) take = 0;                               // ... nor start one
-                    if (take == 0 && per_cta.back().empty()) take = left <= 2 * kMinPieceBlocks ? left : kMinPieceBlocks;
+                    if (take == 0 && per_cta[c].empty() && n_whole == 0) take = left <= 2 * kMinPieceBlocks ? left : kMinPieceBlocks;
                 }
                 if (take > 0) {
-                    per_cta.back().push_back({(int)ui, b, b + take});
+                    per_cta[c].push_back({(int)ui, b, b + take});
                     ++pieces_of_unit[ui];
                     assigned += take * u.w + kItemOverhead;
                     b += take;
                 }
-                if (!last_cta && (b < u.blocks || (double)per_cta.size() * target - assigned < 0.5 * kItemOverhead + 0.5)) per_cta.emplace_back();
+                if (!last_cta && (b < u.blocks || cum[c] - assigned < 0.5 * kItemOverhead + 0.5)) ++c;
             }
         }
-        if (per_cta.back().empty()) per_cta.pop_back();
         size_t items = 0;
         double worst = 0.0;
-        for (const auto& l : per_cta) {
-            items += l.size();
-            double c = 0.0;
-            for (const Piece& pc : l) c += (pc.b1 - pc.b0) * units[pc.unit].w + kItemOverhead;
-            worst = std::max(worst, c);
+        for (int k = 0; k < G; ++k) {
+            items += per_cta[k].size();
+            double cost = load[k];
+            for (const Piece& pc : per_cta[k]) cost += (pc.b1 - pc.b0) * units[pc.unit].w + kItemOverhead;
+            worst = std::max(worst, cost);
         }
         if (worst < best_max) { best_max = worst; best_cta = per_cta; best_pieces = pieces_of_unit; }
         if (items == n_items) break;
@@ -999,14 +1024,38 @@ FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int head
     }
     per_cta.swap(best_cta);
     pieces_of_unit.swap(best_pieces);
+    // Per-CTA order: [later piece (index >= 1) of a cut unit] [whole units, wave by wave, then whole units of the remainder] [head piece (index 0)
+    // of a cut unit].  The kernel's combine protocol needs exactly this: a waited-for piece is the first thing its CTA does, the waiting
+    // head piece the last.
+    for (int k = 0; k < G; ++k) {
+        std::vector<Piece> first, mid, last;
+        for (const Piece& pc : per_cta[k]) {
+            const bool cut = pieces_of_unit[pc.unit] > 1;
+            (cut && pc.b0 > 0 ? first : cut ? last : mid).push_back(pc);
+        }
+        std::vector<Piece> order(first);
+        for (size_t ui = (size_t)k; ui < n_whole; ui += (size_t)G) { order.push_back({(int)ui, 0, units[ui].blocks}); pieces_of_unit[ui] = 1; }
+        order.insert(order.end(), mid.begin(), mid.end());
+        order.insert(order.end(), last.begin(), last.end());
+        per_cta[k].swap(order);
+    }
+    while (!per_cta.empty() && per_cta.back().empty()) per_cta.pop_back();
+    for (auto it = per_cta.begin(); it != per_cta.end();) it = it->empty() ? per_cta.erase(it) : it + 1;
     std::vector<int> slot_of_unit(units.size(), -1), next_piece(units.size(), 0);
     for (size_t ui = 0; ui < units.size(); ++ui)
         if (pieces_of_unit[ui] > 1) { slot_of_unit[ui] = sch.n_slots++; sch.max_pieces = std::max(sch.max_pieces, pieces_of_unit[ui]); }
+    // piece index = rank of the piece's first key block inside its unit (key order), whatever order the CTAs run them in
+    std::vector<std::vector<int>> starts(units.size());
+    for (const auto& list : per_cta)
+        for (const Piece& pc : list) if (pieces_of_unit[pc.unit] > 1) starts[pc.unit].push_back(pc.b0);
+    for (auto& v : starts) std::sort(v.begin(), v.end());
+    (void)next_piece;
     for (const auto& list : per_cta) {
         for (const Piece& pc : list) {
             const Unit& u = units[pc.unit];
             const int lo = u.s0 + pc.b0 * BKV, hi = std::min(u.s1, u.s0 + pc.b1 * BKV);
-            sch.items.push_back({u.q, u.s0, u.s1, u.head, lo, hi, slot_of_unit[pc.unit], next_piece[pc.unit]++ | (pieces_of_unit[pc.unit] << 8)});
+            const int idx = pieces_of_unit[pc.unit] > 1 ? (int)(std::lower_bound(starts[pc.unit].begin(), starts[pc.unit].end(), pc.b0) - starts[pc.unit].begin()) : 0;
+            sch.items.push_back({u.q, u.s0, u.s1, u.head, lo, hi, slot_of_unit[pc.unit], idx | (pieces_of_unit[pc.unit] << 8)});
         }
         sch.cta_ptr.push_back((int)sch.items.size());
     }

@@ -232,11 +232,12 @@ def _fmha_schedule_persistent(cu, n_ctas=148, force=0, heads=8):
 
 @pytest.mark.parametrize("force", [0, 1])
 @pytest.mark.parametrize("cu", [[0, 4096, 8192], [0, 8192], [0, 512, 1024], [0, 16384], [0, 3000, 5000, 9000], [0, 100], [0, 130, 700, 701],
-                                [0, 4096, 8192, 12288, 16384], [0, 200, 336, 408]])
+                                [0, 4096, 8192, 12288, 16384], [0, 200, 336, 408], list(range(0, 8192 * 8 + 1, 8192))])
 def test_fmha_persistent_schedule_tiles_the_work_and_balances_the_ctas(cu, force):
     """Host logic of the default attention launch (one persistent CTA per SM): the items tile (query block, head) x keys exactly once,
-    pieces of a cut unit are contiguous in the keys, share a slot and are numbered 0..n-1, every CTA owns a non-empty contiguous item range,
-    and at the BASELINE shapes no CTA carries more than 3 % above the mean estimated cost (that maximum IS the kernel's duration)."""
+    pieces of a cut unit are contiguous in the keys, share a slot and are numbered 0..n-1 in key order, every CTA owns a non-empty contiguous
+    item range, whole units are dealt wave by wave (unit k*G + c -> CTA c: all CTAs stay inside one window of K/V streams), only the last
+    partial wave is cut, and at the BASELINE shapes no CTA carries more than 3 % above the mean estimated cost (= the kernel's duration)."""
     items, cta_ptr, n_slots, max_pieces = _fmha_schedule_persistent(cu, force=force)
     assert cta_ptr[0] == 0 and cta_ptr[-1] == len(items) and (np.diff(cta_ptr) > 0).all() and len(cta_ptr) - 1 <= 148
     seen = {}
@@ -265,7 +266,13 @@ def test_fmha_persistent_schedule_tiles_the_work_and_balances_the_ctas(cu, force
     blocks = (items[:, 5] - items[:, 4] + 127) // 128
     cost = blocks * np.where(items[:, 0] + 128 < items[:, 2], 1.0, 0.55) + 2.0
     per = np.array([cost[a:b].sum() for a, b in zip(cta_ptr[:-1], cta_ptr[1:])])
+    if len(cu) == 9:      # 8 scenes x 8192: 2048 units = 13 whole waves of 148 + a cut remainder; wave k of CTA c is unit k * 148 + c
+        assert len(per) == 148 and per.max() <= 1.03 * per.mean()
+        whole = items[cta_ptr[7]:cta_ptr[8]]
+        whole = whole[whole[:, 6] < 0]
+        order = [(s0 // 8192) * 8 * 32 + head * 32 + (q0 - s0) // 256 for q0, s0, s1, head, *_ in whole.tolist()]
+        assert order[:13] == [k * 148 + 7 for k in range(13)]
     if cu in ([0, 4096, 8192], [0, 8192], [0, 16384], [0, 4096, 8192, 12288, 16384]):
-        assert len(per) == 148 and per.max() <= 1.03 * per.mean() and n_slots > 0 and max_pieces == 2
+        assert len(per) == 148 and per.max() <= 1.03 * per.mean() and n_slots > 0 and 2 <= max_pieces <= 4
     if cu == [0, 512, 1024] and not force:
         assert n_slots == 0 and len(per) == 32            # small launch: whole units, nothing is cut
