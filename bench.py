@@ -201,10 +201,15 @@ def own_kernel_comparators(dev) -> dict:
     out = torch.empty(T, 512, device=dev, dtype=torch.float16)
     res = {"attention": {}, "gemm": {}}
     for name, cu in (("per_view", [0, PTS, 2 * PTS]), ("per_scene", [0, T])):
-        ms = C.c_float(0)
-        _lib.check(_lib.lib.rap_bench_fmha(qkv.data_ptr(), T, 8, _lib.i32_array(cu), len(cu) - 1, out.data_ptr(), 20, C.byref(ms)), "rap_bench_fmha")
         fl = sum(4.0 * 512 * (e - s) ** 2 for s, e in zip(cu[:-1], cu[1:]))
-        res["attention"][name] = {"rap_ms": ms.value, "rap_tflops": fl / ms.value / 1e9}
+        row = {}
+        # -1: the kernel the product launches (one item per CTA); 1 / 2: the opt-in persistent stream-K kernel, faster as an isolated launch
+        # but not inside the sampler
+        for key, variant in (("rap", -1), ("rap_persistent", 1), ("rap_persistent_contiguous", 2)):
+            ms = C.c_float(0)
+            _lib.check(_lib.lib.rap_bench_fmha_variant(qkv.data_ptr(), T, 8, _lib.i32_array(cu), len(cu) - 1, out.data_ptr(), 20, variant, C.byref(ms)), "rap_bench_fmha")
+            row[key + "_ms"], row[key + "_tflops"] = ms.value, fl / ms.value / 1e9
+        res["attention"][name] = row
     st = torch.cuda.current_stream().cuda_stream
     # (epilogue, tile N, K, N): the four DiT GEMM shapes with the epilogues the product fuses into them
     for name, (epi, bn, K, N) in {"qkv_512x1536 (+qk RMS-norm, fp16 out)": (2, 256, 512, 1536), "out_512x512 (+bias +fp32 residual)": (0, 256, 512, 512),

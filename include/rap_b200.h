@@ -139,6 +139,10 @@ int rap_apply_transform(const void* points, long long n, int is_f64, const doubl
 
 /* Timing aid (tools/fmha_split_sweep.py): mean duration of `iters` back-to-back attention launches on the default stream. */
 int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out, int iters, float* ms_per_launch);
+/* Same for a named kernel variant: -1 what the product launches, 0 one item per CTA (default), 1 persistent stream-K (whole waves dealt round-robin),
+ * 2 persistent with one contiguous range per CTA. */
+int rap_bench_fmha_variant(const void* qkv, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out, int iters, int variant,
+                           float* ms_per_launch);
 
 /* Host-only helper (no GPU): the attention work list of one launch -- (query block, head) units, the units of the last partially filled
  * wave cut along the key axis so every SM finishes together; 8 int32 per item {q_row0, seg_start, seg_end, head, kv_lo, kv_hi, slot,
@@ -146,7 +150,7 @@ int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_seqlens_
 int rap_fmha_schedule(const int32_t* cu_seqlens_host, int n_segments, int heads, int force_split, int32_t* items_out, int capacity,
                       int* n_slots_out, int* max_pieces_out);
 
-/* Host-only helper (no GPU): the PERSISTENT attention schedule the product launches by default -- one CTA per SM, each walking a contiguous,
+/* Host-only helper (no GPU): the PERSISTENT attention schedule (opt-in kernel, RAP_FMHA_PERSIST=1) -- one CTA per SM, each walking a contiguous,
  * equal-cost range of the linearised (query block x head, key block) space; units that straddle a CTA boundary are cut along the keys and
  * recombined by the piece that finishes last.  items as above, ordered by CTA; cta_ptr_out[n_ctas_used + 1] = item range of every CTA.
  * n_ctas <= 0: the SM count of the current device (148 without one).  Returns the number of items. */

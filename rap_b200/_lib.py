@@ -64,6 +64,7 @@ PROTOTYPES = {
     "rap_segment_nn": (C.c_int, [_f32p, _f32p, _vp, C.c_int, _vp, _vp, _f32p, _vp]),
     "rap_apply_transform": (C.c_int, [_vp, C.c_longlong, C.c_int, C.POINTER(C.c_double), _vp, _vp]),
     "rap_bench_fmha": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int, C.POINTER(C.c_float)]),
+    "rap_bench_fmha_variant": (C.c_int, [_vp, C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "rap_fmha_schedule": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rap_fmha_schedule_persistent": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                                C.POINTER(C.c_int)]),

@@ -899,9 +899,15 @@ extern "C" int rap_fmha_schedule_persistent(const int32_t* cu_host, int n_segmen
 }
 
 // Timing aid: `iters` back-to-back launches of one attention call between two events (schedule built once, like a plan does).
-extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, float* ms_per_launch) {
-    RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch, "rap_bench_fmha: bad argument");
-    const FmhaSchedule sch = build_fmha_schedule_auto(std::vector<int>(cu_host, cu_host + n_segments + 1), heads);
+// variant: -1 = what the product launches (RAP_FMHA_PERSIST), 0 = one item per CTA, 1 = persistent wave-major, 2 = persistent contiguous.
+extern "C" int rap_bench_fmha_variant(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, int variant,
+                                      float* ms_per_launch) {
+    RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch && variant >= -1 && variant <= 2, "rap_bench_fmha: bad argument");
+    const std::vector<int> cu(cu_host, cu_host + n_segments + 1);
+    FmhaSchedule sch;
+    if (variant < 0) sch = build_fmha_schedule_auto(cu, heads);
+    else if (variant == 0) sch = build_fmha_schedule(cu, heads);
+    else { g_persist_contiguous_override = variant == 2 ? 1 : 0; sch = build_fmha_schedule_persistent(cu, heads); g_persist_contiguous_override = -1; }
     DevSchedule ds;
     RAP_TRY(ds.upload(sch));
     CUtensorMap tm;
@@ -922,12 +928,18 @@ extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
+extern "C" int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, float* ms_per_launch) {
+    return rap_bench_fmha_variant(qkv, T, heads, cu_host, n_segments, out, iters, -1, ms_per_launch);
+}
 
 extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, int force_split, void* out, void* dbg, void* stream) {
     RAP_REQUIRE(heads == HEADS, "rap_test_fmha: heads must be 8");
     std::vector<int> cu(cu_host, cu_host + n_segments + 1);
-    // force_split = 2: the one-item-per-CTA kernel with its last wave split (the A/B variant), whatever RAP_FMHA_PERSIST says
-    const FmhaSchedule sch = force_split == 2 ? build_fmha_schedule(cu, heads, true) : build_fmha_schedule_auto(cu, heads, force_split != 0);
+    // force_split: 0 / 1 = persistent kernel (wave-major schedule; 1 = tiny per-CTA share so small inputs are cut too), 4 / 5 = the same with one
+    // contiguous range per CTA, 2 = one item per CTA with the last wave force-split, 3 = one item per CTA as the product launches it
+    FmhaSchedule sch;
+    if (force_split == 2 || force_split == 3) sch = build_fmha_schedule(cu, heads, force_split == 2);
+    else { g_persist_contiguous_override = force_split >= 4 ? 1 : 0; sch = build_fmha_schedule_persistent(cu, heads, 0, (force_split & 1) != 0); g_persist_contiguous_override = -1; }
     DevSchedule ds;
     RAP_TRY(ds.upload(sch));
     CUtensorMap tm;

@@ -899,11 +899,20 @@ FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool for
     return sch;
 }
 
-bool fmha_persistent_enabled() {
+// RAP_FMHA_PERSIST: 0 / unset = one item per CTA, hardware-scheduled, last wave key-split (default); 1 = persistent stream-K kernel, whole waves
+// dealt round-robin; 2 = persistent, one contiguous range per CTA.  The persistent kernel is 6-9 % faster as an isolated launch (r02: 94.6 /
+// 171.8 us against 104.7 / 186.8) but NOT inside the sampler (same-box alternating A/B, ms per pair at 1 pair | ms per step at 8 pairs:
+// default 98.52 / 98.13 | 760.8 / 760.6; =1: 99.97 / 100.21 | 776.9 / 776.8; =2: 98.87 / 98.93 | 834.4 / 835.9): under programmatic dependent
+// launch the ragged end of a hardware-scheduled grid lets the next kernel's CTAs start (and run their prologues) while the last ones
+// finish, whereas 148 persistent CTAs end together and the step is power-capped anyway.
+int fmha_persist_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("RAP_FMHA_PERSIST"); v = (e && atoi(e) == 0) ? 0 : 1; }
-    return v == 1 && fmha_rows_per_cta() == 256;
+    if (v < 0) { const char* e = getenv("RAP_FMHA_PERSIST"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; }
+    return fmha_rows_per_cta() == 256 ? v : 0;
 }
+bool fmha_persistent_enabled() { return fmha_persist_mode() != 0; }
+
+int g_persist_contiguous_override = -1;               // rap_bench_fmha_variant / tests: force the contiguous (1) or wave-major (0) persistent schedule
 
 // Cost model of the persistent schedule, in units of one 128-key block of a 256-row unit (~2.5 k cycles): a unit whose second query tile
 // is empty keeps only one softmax warpgroup busy; every item pays a fixed start/drain cost (first scores, row max, epilogue, Q reload).
@@ -960,7 +969,8 @@ FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int head
     // (scene, head) stream at once -- 128 MB of K/V at 8 pairs -- and thrash L2).  Only the LAST, partial wave is cut stream-K style, each
     // CTA receiving what it is short of the common target.
     const size_t U = units.size();
-    const size_t n_whole = (U / (size_t)G) * (size_t)G;
+    const bool contiguous = g_persist_contiguous_override >= 0 ? g_persist_contiguous_override == 1 : fmha_persist_mode() == 2;
+    const size_t n_whole = contiguous ? 0 : (U / (size_t)G) * (size_t)G;
     std::vector<double> load((size_t)G, 0.0);
     for (size_t ui = 0; ui < n_whole; ++ui) load[ui % (size_t)G] += units[ui].blocks * units[ui].w + kItemOverhead;
     double rem_work = 0.0;

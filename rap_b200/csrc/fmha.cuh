@@ -29,14 +29,15 @@ struct FmhaSchedule {
 // force_split (tests): cut the last wave even where the cost model says it does not pay.
 FmhaSchedule build_fmha_schedule(const std::vector<int>& cu, int heads, bool force_split = false);
 
-// Persistent ("stream-K") schedule, the default: ONE CTA per SM, each walking a contiguous range of the linearised (unit, key block)
+// Persistent ("stream-K") schedule (opt-in, RAP_FMHA_PERSIST=1|2; faster as an isolated launch, not inside the sampler): ONE CTA per SM, each walking a contiguous range of the linearised (unit, key block)
 // space of equal estimated cost, so that every SM finishes together whatever the number of (query block, head) units is -- 256 units on
 // 148 SMs (cfg2) otherwise waste a quarter of the second wave.  A unit that straddles a CTA boundary is cut along its keys; its pieces
 // leave un-normalised partial rows in the workspace and the piece that finishes last combines them in piece order (deterministic).
 // No CTA ever waits for another one.  n_ctas <= 0: one per SM.  force_split (tests): tiny per-CTA budget so that small inputs are cut too.
-// RAP_FMHA_PERSIST=0 selects the one-item-per-CTA kernel above instead (A/B measurements).
+// Default is the one-item-per-CTA kernel above.
 FmhaSchedule build_fmha_schedule_persistent(const std::vector<int>& cu, int heads, int n_ctas = 0, bool force_split = false);
 bool fmha_persistent_enabled();
+extern int g_persist_contiguous_override;   // -1: as RAP_FMHA_PERSIST says; 0 / 1: wave-major / contiguous persistent schedule (micro entry points)
 // The schedule the product uses for this layout (persistent unless disabled).
 FmhaSchedule build_fmha_schedule_auto(const std::vector<int>& cu, int heads, bool force_split = false);
 

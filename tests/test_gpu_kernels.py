@@ -133,9 +133,10 @@ def test_gemm_geglu(rap):
     assert (out16.float() - ref).abs().max().item() < 2e-2
 
 
-# force=0: the product schedule (persistent CTAs, units cut where a CTA's share ends); force=1: a tiny per-CTA share, so small inputs are
-# cut into pieces and recombined too; force=2: the one-item-per-CTA kernel with its last wave split (the RAP_FMHA_PERSIST=0 variant)
-@pytest.mark.parametrize("force", [0, 1, 2])
+# force=3: the kernel the product launches (one item per CTA), 2: with its last wave force-split; 0 / 1: the opt-in persistent stream-K kernel
+# (wave-major schedule; 1 = a tiny per-CTA share, so small inputs are cut into pieces and recombined too); 4 / 5: the same with one
+# contiguous range per CTA
+@pytest.mark.parametrize("force", [3, 2, 0, 1, 4, 5])
 @pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048], [512, 512], [2000, 1500],
                                   [4096, 4096], [8192], [16384]])
 def test_fmha_varlen(rap, lens, force):
@@ -156,7 +157,8 @@ def test_fmha_varlen(rap, lens, force):
     assert err < 1e-2, f"max err {err}"
 
 
-def test_fmha_lazy_reference_overflow_path(rap):
+@pytest.mark.parametrize("force", [2, 1])
+def test_fmha_lazy_reference_overflow_path(rap, force):
     """Adversarial scores for the lazy reference exponent: the first K/V block scores ~0, later blocks reach 2^40 times more, so
     the stale-reference pass must detect fp16 overflow of P and take the re-reference + O/l rescale path (several times)."""
     g = torch.Generator("cuda").manual_seed(11)
@@ -167,7 +169,7 @@ def test_fmha_lazy_reference_overflow_path(rap):
     qkv[128:384, 1] *= 0.3                                       # intermediate growth
     qkv = qkv.half().contiguous()
     out = torch.zeros(T, 512, device="cuda", dtype=torch.float16)
-    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array([0, T]), 1, 1, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
+    rap.check(rap.lib.rap_test_fmha(qkv.data_ptr(), T, 8, rap.i32_array([0, T]), 1, force, out.data_ptr(), None, rap.stream_ptr()), "rap_test_fmha")
     _sync_check(rap)
     q, k, v = (qkv[:, i].float().transpose(0, 1) for i in range(3))
     ref = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1)
