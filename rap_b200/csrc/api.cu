@@ -937,7 +937,10 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
     std::vector<int> cu(cu_host, cu_host + n_segments + 1);
     // force_split: 0 / 1 = persistent kernel (wave-major schedule; 1 = tiny per-CTA share so small inputs are cut too), 4 / 5 = the same with one
     // contiguous range per CTA, 2 = one item per CTA with the last wave force-split, 3 = one item per CTA as the product launches it
+    // 6 / 7 = as 2 / 3 with a second UMMA-issuing warp (one per query tile)
     FmhaSchedule sch;
+    const bool mma2 = force_split == 6 || force_split == 7;
+    if (mma2) force_split -= 4;
     if (force_split == 2 || force_split == 3) sch = build_fmha_schedule(cu, heads, force_split == 2);
     else { g_persist_contiguous_override = force_split >= 4 ? 1 : 0; sch = build_fmha_schedule_persistent(cu, heads, 0, (force_split & 1) != 0); g_persist_contiguous_override = -1; }
     DevSchedule ds;
@@ -948,6 +951,7 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
         FmhaArgs f{};
         f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
         f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
+        f.mma2 = mma2 ? 1 : 0;
         f.gen = 1;
         rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));
         f.gen = 2;                                                                                          // a second launch on the same workspace:

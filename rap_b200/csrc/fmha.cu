@@ -49,7 +49,7 @@ constexpr float kRowSumLimit = 32768.0f;         // a block row sum >= 2^15 mean
 // exponentiates block j of tile 0, the tensor core produces tile 1's scores and vice versa: the exp (MUFU) pipe, which
 // bounds head_dim-64 attention, stays busy and each K/V block is fetched once for 256 query rows.
 template <int NT>
-__global__ void __launch_bounds__(FCfg<NT>::kThreads, 3 - NT)
+__global__ void __launch_bounds__(FCfg<NT>::kThreads + (NT == 2 ? 32 : 0), 3 - NT)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     using F = FCfg<NT>;
     constexpr int KV_STAGES = F::KV_STAGES, OFF_Q = F::OFF_Q, OFF_K = F::OFF_K, OFF_V = F::OFF_V, OFF_BAR = F::OFF_BAR;
@@ -65,6 +65,9 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
     const int kv_begin = item.kv_lo, kv_end = item.kv_hi;            // this piece's keys (the whole segment unless the unit was split)
     const int n_kv = (kv_end - kv_begin + BKV - 1) / BKV;
     const bool two = NT == 2 && q0 + BQ < seg_end; // second 128-row tile has rows inside the segment
+    // mma2: each query tile has its OWN UMMA-issuing warp (warp 1: tile 0, warp 10: tile 1).  One warp issuing for both tiles blocks on the
+    // in-order tensor queue (issuing tile 0's P.V, 8 UMMAs behind its QK^T) while tile 1's scores could already be requested, and vice versa.
+    const bool mma2 = NT == 2 && p.mma2 && two && blockDim.x > (unsigned)FCfg<NT>::kThreads;
 
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t q_full = bar;
@@ -82,7 +85,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
         if (sbase & 1023u) { atomicCAS(&g_dev_error, 0u, 0xA1u); __trap(); }
         tma_prefetch_desc(&tm_qkv);
         mbar_init(q_full, 1);
-        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), mma2 ? 2 : 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), mma2 ? 2 : 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
         mbar_fence_init();
     }
@@ -117,13 +120,15 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             }
             if (++s == KV_STAGES) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 1) {
-        // Whole warp converged; only the UMMA / commit instructions are predicated on the elected lane.
+    } else if (warp == 1 || warp == 10) {
+        // Whole warp converged; only the UMMA / commit instructions are predicated on the elected lane.  Tiles [t_lo, t_hi) of this warp:
+        // both for warp 1 alone, one each with mma2.
+        const int nt = two ? 2 : 1;
+        const int t_lo = (warp == 10) ? 1 : 0, t_hi = mma2 ? t_lo + 1 : (warp == 10 ? 0 : nt);     // (warp 10 idles unless mma2)
         const bool leader = elect_one();
-        const bool dbg_on = p.dbg && blockIdx.x == 0 && leader;
+        const bool dbg_on = p.dbg && blockIdx.x == 0 && leader && warp == 1;
         constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BKV, false, false);   // A=Q K-major, B=K K-major, N=128
         constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A=P K-major, B=V MN-major, N=64
-        const int nt = two ? 2 : 1;
         auto issue_qk = [&](int t, int s) {
             const uint64_t dq = umma_desc_sw128(sbase + OFF_Q + t * TILE_BYTES, 1024);
             const uint64_t dk = umma_desc_sw128(sbase + OFF_K + s * TILE_BYTES, 1024);
@@ -133,40 +138,42 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
                 umma_commit(s_full(t));
             }
         };
-        mbar_wait(q_full, 0, 0x50);
-        mbar_wait(k_full(0), 0, 0x51);
-        tc_fence_after();
-        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
-        if (leader) umma_commit(k_empty(0));
-        int s = 0; uint32_t ph = 0;                      // stage / phase of K/V block j
-        for (int j = 0; j < n_kv; ++j) {
-            const int s1 = (s + 1 == KV_STAGES) ? 0 : s + 1;
-            const uint32_t ph1 = (s + 1 == KV_STAGES) ? ph ^ 1 : ph;
-            const bool more = j + 1 < n_kv;
-            const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES, 1024);
-            for (int t = 0; t < nt; ++t) {
-                if (more) {                              // next scores of this tile as soon as its softmax is done with S_t(j)
-                    if (t == 0) mbar_wait(k_full(s1), ph1, 0x53);
-                    mbar_wait(s_free(t), j & 1, 0x55);
+        if (t_lo < t_hi) {
+            mbar_wait(q_full, 0, 0x50);
+            mbar_wait(k_full(0), 0, 0x51);
+            tc_fence_after();
+            for (int t = t_lo; t < t_hi; ++t) issue_qk(t, 0);
+            if (leader) umma_commit(k_empty(0));             // (with mma2 the stage is free when both warps' commits have arrived)
+            int s = 0; uint32_t ph = 0;                      // stage / phase of K/V block j
+            for (int j = 0; j < n_kv; ++j) {
+                const int s1 = (s + 1 == KV_STAGES) ? 0 : s + 1;
+                const uint32_t ph1 = (s + 1 == KV_STAGES) ? ph ^ 1 : ph;
+                const bool more = j + 1 < n_kv;
+                const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * TILE_BYTES, 1024);
+                for (int t = t_lo; t < t_hi; ++t) {
+                    if (more) {                              // next scores of this tile as soon as its softmax is done with S_t(j)
+                        if (t == t_lo) mbar_wait(k_full(s1), ph1, 0x53);
+                        mbar_wait(s_free(t), j & 1, 0x55);
+                        tc_fence_after();
+                        FMHA_TS(8 + 4 * t);
+                        issue_qk(t, s1);
+                        if (t == t_hi - 1 && leader) umma_commit(k_empty(s1));
+                    }
+                    FMHA_TS(9 + 4 * t);
+                    if (t == t_lo) mbar_wait(v_full(s), ph, 0x54);
+                    mbar_wait(p_full(t), j & 1, 0x52);       // P_t(j) in TMEM, O_t rescaled if needed
                     tc_fence_after();
-                    FMHA_TS(8 + 4 * t);
-                    issue_qk(t, s1);
-                    if (t == nt - 1 && leader) umma_commit(k_empty(s1));
-                }
-                FMHA_TS(9 + 4 * t);
-                if (t == 0) mbar_wait(v_full(s), ph, 0x54);
-                mbar_wait(p_full(t), j & 1, 0x52);       // P_t(j) in TMEM, O_t rescaled if needed
-                tc_fence_after();
-                if (leader) {
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)   // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 rows (encoded >> 4)
-                        umma_f16_ts(tmem + t * TM_TILE + TM_O, tmem + t * TM_TILE + TM_P + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
-                    umma_commit(pv_done(t));
-                    if (t == nt - 1) umma_commit(v_empty(s));
+                        for (int k = 0; k < BKV / 16; ++k)   // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 rows (encoded >> 4)
+                            umma_f16_ts(tmem + t * TM_TILE + TM_O, tmem + t * TM_TILE + TM_P + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+                        umma_commit(pv_done(t));
+                        if (t == t_hi - 1) umma_commit(v_empty(s));
+                    }
+                    FMHA_TS(10 + 4 * t);
                 }
-                FMHA_TS(10 + 4 * t);
+                s = s1; ph = ph1;
             }
-            s = s1; ph = ph1;
         }
     } else {
         const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
@@ -817,7 +824,7 @@ static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_items, c
         configured = true;
     }
     ProfScope _ps(KC_FMHA, st);
-    RAP_CUDA(launch_pdl(fmha_kernel<NT>, dim3(n_items), dim3(F::kThreads), F::SMEM_BYTES, st, tm_qkv, a));
+    RAP_CUDA(launch_pdl(fmha_kernel<NT>, dim3(n_items), dim3(F::kThreads + ((NT == 2 && a.mma2) ? 32 : 0)), F::SMEM_BYTES, st, tm_qkv, a));
     note_launch();
     return RAP_OK;
 }
@@ -1091,7 +1098,10 @@ int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaSt
     }
     static int early = -1;
     if (early < 0) { const char* e = getenv("RAP_FMHA_EARLY"); early = (e && atoi(e) == 1) ? 1 : 0; }
+    static int mma2 = -1;                                // RAP_FMHA_MMA2: one UMMA-issuing warp per query tile (A/B)
+    if (mma2 < 0) { const char* e = getenv("RAP_FMHA_MMA2"); mma2 = e ? (atoi(e) != 0 ? 1 : 0) : 0; }
     FmhaArgs b = a;
+    b.mma2 = (a.mma2 || mma2) ? 1 : 0;
     b.early_release = early && a.score_bound;
     return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, b, n_ctas, st) : launch_t<2>(tm_qkv, b, n_ctas, st);
 }
