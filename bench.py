@@ -205,7 +205,7 @@ def own_kernel_comparators(dev) -> dict:
         row = {}
         # -1: the kernel the product launches (one item per CTA); 1 / 2: the opt-in persistent stream-K kernel, faster as an isolated launch
         # but not inside the sampler
-        for key, variant in (("rap", -1), ("rap_persistent", 1), ("rap_persistent_contiguous", 2)):
+        for key, variant in (("rap", -1), ("rap_persistent", 1), ("rap_persistent_contiguous", 2), ("rap_3tile_64key", 3)):
             ms = C.c_float(0)
             _lib.check(_lib.lib.rap_bench_fmha_variant(qkv.data_ptr(), T, 8, _lib.i32_array(cu), len(cu) - 1, out.data_ptr(), 20, variant, C.byref(ms)), "rap_bench_fmha")
             row[key + "_ms"], row[key + "_tflops"] = ms.value, fl / ms.value / 1e9

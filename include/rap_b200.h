@@ -140,7 +140,7 @@ int rap_apply_transform(const void* points, long long n, int is_f64, const doubl
 /* Timing aid (tools/fmha_split_sweep.py): mean duration of `iters` back-to-back attention launches on the default stream. */
 int rap_bench_fmha(const void* qkv, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out, int iters, float* ms_per_launch);
 /* Same for a named kernel variant: -1 what the product launches, 0 one item per CTA (default), 1 persistent stream-K (whole waves dealt round-robin),
- * 2 persistent with one contiguous range per CTA. */
+ * 2 persistent with one contiguous range per CTA, 3 three query tiles per CTA on 64-key blocks (RAP_FMHA_NT=3). */
 int rap_bench_fmha_variant(const void* qkv, int T, int heads, const int32_t* cu_seqlens_host, int n_segments, void* out, int iters, int variant,
                            float* ms_per_launch);
 

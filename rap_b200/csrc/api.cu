@@ -388,7 +388,7 @@ struct rap_plan {
     float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
     __half *x16 = nullptr, *attn16 = nullptr, *qkv = nullptr, *ffmid = nullptr, *a_s = nullptr, *a_x = nullptr, *hh16 = nullptr, *y1 = nullptr, *y2 = nullptr;
     float *ada_e0 = nullptr, *ada_e1 = nullptr, *ada_e2 = nullptr, *ada_tab = nullptr;
-    CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn;
+    CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn, tm_qkv_attn64;
     const float* cond = nullptr;
     const uint8_t* anchor = nullptr;
     bool condition_set = false;
@@ -479,6 +479,7 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_hh16, pl->hh16, T, D, D, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_y1, pl->y1, T, D, D, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_qkv_attn, pl->qkv, T, 3 * D, 3 * D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&pl->tm_qkv_attn64, pl->qkv, T, 3 * D, 3 * D, 64);
     if (rc) { cudaFree(pl->ws); delete pl; return rc; }
     *out = pl;
     return RAP_OK;
@@ -617,7 +618,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             f.score_bound = d->score_bound + (size_t)(2 * l + b) * HEADS;
             if (++pl->fmha_gen <= 0) pl->fmha_gen = 1;
             f.gen = pl->fmha_gen;
-            RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st));
+            RAP_TRY(launch_fmha(pl->tm_qkv_attn, f, b == 0 ? pl->n_items_part : pl->n_items_batch, st, &pl->tm_qkv_attn64));
             GemmArgs o{};
             o.M = T; o.N = D; o.K = D; o.bias = d->bout[b][l]; o.addend = pl->h; o.out32 = pl->h; o.ld32 = D;
             RAP_TRY(residual_gemm(o, pl->tm_attn16, d->tm_out[b][l], b == 0 ? 2 * l + 1 : -1 - l, true));   // + LN for the global block / the feed-forward
@@ -902,25 +903,28 @@ extern "C" int rap_fmha_schedule_persistent(const int32_t* cu_host, int n_segmen
 // variant: -1 = what the product launches (RAP_FMHA_PERSIST), 0 = one item per CTA, 1 = persistent wave-major, 2 = persistent contiguous.
 extern "C" int rap_bench_fmha_variant(const void* qkv, int T, int heads, const int32_t* cu_host, int n_segments, void* out, int iters, int variant,
                                       float* ms_per_launch) {
-    RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch && variant >= -1 && variant <= 2, "rap_bench_fmha: bad argument");
+    RAP_REQUIRE(heads == HEADS && iters > 0 && ms_per_launch && variant >= -1 && variant <= 3, "rap_bench_fmha: bad argument");
     const std::vector<int> cu(cu_host, cu_host + n_segments + 1);
     FmhaSchedule sch;
+    struct RowsGuard { ~RowsGuard() { g_fmha_rows_override = 0; } } rows_guard;
+    if (variant >= 0) g_fmha_rows_override = variant == 3 ? 384 : 256;
     if (variant < 0) sch = build_fmha_schedule_auto(cu, heads);
-    else if (variant == 0) sch = build_fmha_schedule(cu, heads);
+    else if (variant == 0 || variant == 3) sch = build_fmha_schedule(cu, heads);
     else { g_persist_contiguous_override = variant == 2 ? 1 : 0; sch = build_fmha_schedule_persistent(cu, heads); g_persist_contiguous_override = -1; }
     DevSchedule ds;
     RAP_TRY(ds.upload(sch));
-    CUtensorMap tm;
+    CUtensorMap tm, tm64;
     RAP_TRY(make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128));
+    RAP_TRY(make_tmap_f16_sw128(&tm64, qkv, T, 3 * D, 3 * D, 64));
     FmhaArgs f{};
     f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
     f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = RAP_OK;
-    for (int i = 0; i < 3 && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr); }
+    for (int i = 0; i < 3 && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr, &tm64); }
     cudaEventRecord(e0, nullptr);
-    for (int i = 0; i < iters && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr); }
+    for (int i = 0; i < iters && !rc; ++i) { ++f.gen; rc = launch_fmha(tm, f, sch.n_ctas(), nullptr, &tm64); }
     cudaEventRecord(e1, nullptr);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(ms_per_launch, e0, e1);
@@ -938,24 +942,30 @@ extern "C" int rap_test_fmha(const void* qkv, int T, int heads, const int32_t* c
     // force_split: 0 / 1 = persistent kernel (wave-major schedule; 1 = tiny per-CTA share so small inputs are cut too), 4 / 5 = the same with one
     // contiguous range per CTA, 2 = one item per CTA with the last wave force-split, 3 = one item per CTA as the product launches it
     // 6 / 7 = as 2 / 3 with a second UMMA-issuing warp (one per query tile)
+    // 8 / 9 = the three-tile kernel (384 query rows per CTA, 64-key blocks), last wave as the cost model says / force-split
     FmhaSchedule sch;
+    struct RowsGuard { ~RowsGuard() { g_fmha_rows_override = 0; } } rows_guard;
+    g_fmha_rows_override = (force_split == 8 || force_split == 9) ? 384 : 256;
+    if (force_split == 8) force_split = 3;
+    if (force_split == 9) force_split = 2;
     const bool mma2 = force_split == 6 || force_split == 7;
     if (mma2) force_split -= 4;
     if (force_split == 2 || force_split == 3) sch = build_fmha_schedule(cu, heads, force_split == 2);
     else { g_persist_contiguous_override = force_split >= 4 ? 1 : 0; sch = build_fmha_schedule_persistent(cu, heads, 0, (force_split & 1) != 0); g_persist_contiguous_override = -1; }
     DevSchedule ds;
     RAP_TRY(ds.upload(sch));
-    CUtensorMap tm;
+    CUtensorMap tm, tm64;
     int rc = make_tmap_f16_sw128(&tm, qkv, T, 3 * D, 3 * D, 128);
+    if (!rc) rc = make_tmap_f16_sw128(&tm64, qkv, T, 3 * D, 3 * D, 64);
     if (!rc) {
         FmhaArgs f{};
         f.items = ds.items; f.cta_ptr = ds.cta_ptr; f.ws = ds.ws; f.counters = ds.counters; f.ws_pieces = sch.max_pieces;
         f.out = static_cast<__half*>(out); f.d_model = D; f.scale_log2 = 1.4426950408889634f / 8.0f; f.dbg = static_cast<long long*>(dbg);
         f.mma2 = mma2 ? 1 : 0;
         f.gen = 1;
-        rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));
+        rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream), &tm64);
         f.gen = 2;                                                                                          // a second launch on the same workspace:
-        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream));   // counters reset / stale row flags ignored
+        if (!rc && sch.n_slots) rc = launch_fmha(tm, f, sch.n_ctas(), static_cast<cudaStream_t>(stream), &tm64);   // counters reset / stale row flags ignored
     }
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     return rc;

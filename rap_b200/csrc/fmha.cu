@@ -403,6 +403,316 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
 }
 
 
+// ======================================================================================= three query tiles, 64-key blocks (RAP_FMHA_NT=3)
+// The two-tile kernel keeps TWO softmax warps on every scheduler; whenever one of them is loading scores / storing P / waiting, the other
+// streams its exponentials alone at ~12.5 cycles per MUFU instruction instead of the pipe's 8, which is where its 18 % to the MUFU bound go
+// (tools/fmha_timeline.py; removing the waits with a second UMMA warp only moved the time into MUFU contention).  Here a CTA owns THREE
+// 128-row query tiles (384 rows) of one head and walks 64-key blocks, so three softmax warps share each scheduler: TMEM per tile = S 64 + P 32
+// + O 64 columns (3 x 160 = 480 of 512), 14 warps (TMA, UMMA, 3 x 4 softmax).  Everything else -- stale reference exponent, overflow path,
+// TS-mode P.V, key-split units with the handshake combine -- is the two-tile kernel's.
+namespace k3 {
+constexpr int NT = 3, BK3 = 64, STAGES = 6;
+constexpr int KV_TILE = BK3 * HD * 2;                  // 8 KB: 64 keys x 128 bytes
+constexpr int OFF_Q = 0, OFF_K = NT * TILE_BYTES, OFF_V = OFF_K + STAGES * KV_TILE, OFF_BAR = OFF_V + STAGES * KV_TILE;
+constexpr int SMEM_BYTES = OFF_BAR + 512;
+constexpr int kThreads = 64 + NT * 128;
+constexpr uint32_t TM_TILE3 = 160, TM_S3 = 0, TM_P3 = 64, TM_O3 = 96;
+}  // namespace k3
+
+__global__ void __launch_bounds__(k3::kThreads, 1)
+fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const FmhaArgs p) {
+    using namespace k3;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const FmhaItem item = p.items[blockIdx.x];
+    const int head = item.head, q0 = item.q_row0, seg_end = item.seg_end;
+    const int kv_begin = item.kv_lo, kv_end = item.kv_hi;
+    const int n_kv = (kv_end - kv_begin + BK3 - 1) / BK3;
+    const int nt = min(NT, (seg_end - q0 + BQ - 1) / BQ);           // query tiles with rows inside the segment
+
+    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t q_full = bar;
+    auto k_full = [&](int s) { return bar + 8 + 8 * s; };
+    auto k_empty = [&](int s) { return bar + 56 + 8 * s; };
+    auto v_full = [&](int s) { return bar + 104 + 8 * s; };
+    auto v_empty = [&](int s) { return bar + 152 + 8 * s; };
+    auto s_full = [&](int t) { return bar + 200 + 8 * t; };
+    auto p_full = [&](int t) { return bar + 224 + 8 * t; };
+    auto pv_done = [&](int t) { return bar + 248 + 8 * t; };
+    auto s_free = [&](int t) { return bar + 272 + 8 * t; };
+    const uint32_t tmem_slot = bar + 296;
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023u) { atomicCAS(&g_dev_error, 0u, 0xA1u); __trap(); }
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+        for (int t = 0; t < NT; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 296);
+    const int col_q = head * HD, col_k = p.d_model + head * HD, col_v = 2 * p.d_model + head * HD;
+    pdl_wait();                                    // qkv comes from the previous kernel
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        if (leader) {
+            mbar_expect_tx(q_full, nt * TILE_BYTES);
+            for (int t = 0; t < nt; ++t) tma_load_2d(sbase + OFF_Q + t * TILE_BYTES, &tm_q, q_full, col_q, q0 + t * BQ);
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < n_kv; ++j) {
+            const int row = kv_begin + j * BK3;
+            mbar_wait(k_empty(s), ph ^ 1, 0x41);
+            if (leader) { mbar_expect_tx(k_full(s), KV_TILE); tma_load_2d(sbase + OFF_K + s * KV_TILE, &tm_kv, k_full(s), col_k, row); }
+            mbar_wait(v_empty(s), ph ^ 1, 0x42);
+            if (leader) { mbar_expect_tx(v_full(s), KV_TILE); tma_load_2d(sbase + OFF_V + s * KV_TILE, &tm_kv, v_full(s), col_v, row); }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BK3, false, false);   // A = Q (K-major), B = K (K-major), N = 64 keys
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A = P (TMEM), B = V (MN-major), N = 64 dims
+        auto issue_qk = [&](int t, int s) {
+            const uint64_t dq = umma_desc_sw128(sbase + OFF_Q + t * TILE_BYTES, 1024);
+            const uint64_t dk = umma_desc_sw128(sbase + OFF_K + s * KV_TILE, 1024);
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem + t * TM_TILE3 + TM_S3, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                umma_commit(s_full(t));
+            }
+        };
+        mbar_wait(q_full, 0, 0x50);
+        mbar_wait(k_full(0), 0, 0x51);
+        tc_fence_after();
+        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
+        if (leader) umma_commit(k_empty(0));
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < n_kv; ++j) {
+            const int s1 = (s + 1 == STAGES) ? 0 : s + 1;
+            const uint32_t ph1 = (s + 1 == STAGES) ? ph ^ 1 : ph;
+            const bool more = j + 1 < n_kv;
+            const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * KV_TILE, 1024);
+            for (int t = 0; t < nt; ++t) {
+                if (more) {
+                    if (t == 0) mbar_wait(k_full(s1), ph1, 0x53);
+                    mbar_wait(s_free(t), j & 1, 0x55);
+                    tc_fence_after();
+                    issue_qk(t, s1);
+                    if (t == nt - 1 && leader) umma_commit(k_empty(s1));
+                }
+                if (t == 0) mbar_wait(v_full(s), ph, 0x54);
+                mbar_wait(p_full(t), j & 1, 0x52);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < BK3 / 16; ++k)       // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 keys (encoded >> 4)
+                        umma_f16_ts(tmem + t * TM_TILE3 + TM_O3, tmem + t * TM_TILE3 + TM_P3 + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+                    umma_commit(pv_done(t));
+                    if (t == nt - 1) umma_commit(v_empty(s));
+                }
+            }
+            s = s1; ph = ph1;
+        }
+    } else {
+        const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
+        const int qd = warp & 3;                         // TMEM lane quarter of this warp
+        const int r = qd * 32 + lane;                    // query row inside the tile
+        if (t < nt) {
+            const uint32_t t_lane = tmem + (uint32_t(qd * 32) << 16);
+            const uint32_t tm_s = t_lane + t * TM_TILE3 + TM_S3, tm_p = t_lane + t * TM_TILE3 + TM_P3, tm_o = t_lane + t * TM_TILE3 + TM_O3;
+            const float sl2 = p.scale_log2;
+            float m_run = -INFINITY, l_run = 0.f;
+            uint32_t sreg[2][32];
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(s_full(t), j & 1, 0x61);
+                tc_fence_after();
+                const int valid = kv_end - (kv_begin + j * BK3);
+                tmem_ld32(tm_s, sreg[0]);
+                tmem_ld32(tm_s + 32, sreg[1]);
+                tmem_ld_wait();
+                if (valid < BK3) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) sreg[c][i] = 0xff800000u;   // -inf
+                }
+                if (j == 0) {
+                    float mxa[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sreg[c][i]));
+                    m_run = sl2 * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+                }
+                const bool pv_ready = j == 0 || mbar_try_wait(pv_done(t), (j - 1) & 1);
+                f32x2 ls[4] = {0ull, 0ull, 0ull, 0ull};
+                const f32x2 sl2x2 = pack2(sl2, sl2), nmx2 = pack2(-m_run, -m_run);
+                uint32_t preg[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float ua, ub;
+                        unpack2(ffma2(pack2(__uint_as_float(sreg[c][i]), __uint_as_float(sreg[c][i + 1])), sl2x2, nmx2), ua, ub);
+                        const float a = ex2f(ua), b = ex2f(ub);
+                        ls[(i >> 1) & 3] = fadd2(ls[(i >> 1) & 3], pack2(a, b));
+                        preg[c * 16 + i / 2] = pack_half2(a, b);
+                    }
+                }
+                float lsum;
+                {
+                    float s0, s1;
+                    unpack2(fadd2(fadd2(ls[0], ls[1]), fadd2(ls[2], ls[3])), s0, s1);
+                    lsum = s0 + s1;
+                }
+                const bool grow = !(lsum < kRowSumLimit);
+                const bool slow = __any_sync(0xffffffffu, grow);
+                if (!slow) {
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
+                if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(pv_done(t), (j - 1) & 1, 0x62);
+                tc_fence_after();
+                if (slow) {
+                    float bmax = -INFINITY;
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, (c * 32 + i < valid) ? __uint_as_float(sreg[0][i]) : -INFINITY);
+                    }
+                    const float m_new = grow ? bmax * sl2 : m_run;
+                    const float alpha = ex2f(m_run - m_new);
+                    m_run = m_new;
+                    l_run *= alpha;
+                    lsum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        tmem_ld32(tm_s + c * 32, sreg[0]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const bool v0 = c * 32 + i < valid, v1 = c * 32 + i + 1 < valid;
+                            const float a = v0 ? ex2f(fmaf(__uint_as_float(sreg[0][i]), sl2, -m_run)) : 0.f;
+                            const float b = v1 ? ex2f(fmaf(__uint_as_float(sreg[0][i + 1]), sl2, -m_run)) : 0.f;
+                            lsum += a + b;
+                            preg[c * 16 + i / 2] = pack_half2(a, b);
+                        }
+                    }
+                    if (j > 0) {
+                        uint32_t o[8];
+#pragma unroll 1
+                        for (int c = 0; c < HD / 8; ++c) {
+                            tmem_ld8(tm_o + c * 8, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st8(tm_o + c * 8, o);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free(t));
+                }
+                l_run += lsum;
+                tmem_st32(tm_p, preg);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(t));
+            }
+            // epilogue
+            mbar_wait(pv_done(t), (n_kv - 1) & 1, 0x63);
+            tc_fence_after();
+            const int row = q0 + t * BQ + r;
+            uint32_t o[32], o2[32];
+            tmem_ld32(tm_o, o);
+            tmem_ld32(tm_o + 32, o2);
+            tmem_ld_wait();
+            bool write_out = true;
+            if (item.slot >= 0) {
+                const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
+                const int nthreads = nt * 128;
+                float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
+                float4* mine = reinterpret_cast<float4*>(unit_ws + ((size_t)piece * (NT * BQ) + t * BQ + r) * kWsRow);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mine[i / 4] = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+                    mine[8 + i / 4] = make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3]));
+                }
+                mine[16] = make_float4(m_run, l_run, 0.f, 0.f);
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                if (warp == 2 && lane == 0) {
+                    const int arrived = atomicAdd(p.counters + item.slot, 1);
+                    if (arrived == n_pieces - 1) p.counters[item.slot] = 0;
+                    *reinterpret_cast<volatile int*>(smem + OFF_BAR + 304) = arrived == n_pieces - 1;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+                write_out = *reinterpret_cast<volatile int*>(smem + OFF_BAR + 304) != 0;
+                if (write_out) {
+                    __threadfence();
+                    const float* rows = unit_ws + (size_t)(t * BQ + r) * kWsRow;
+                    const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
+                    float m_all = -INFINITY;
+                    for (int q = 0; q < n_pieces; ++q) m_all = fmaxf(m_all, __ldcg(rows + q * piece_stride + 64));
+                    l_run = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { o[i] = 0u; o2[i] = 0u; }
+                    for (int q = 0; q < n_pieces; ++q) {
+                        const float4* src = reinterpret_cast<const float4*>(rows + q * piece_stride);
+                        const float4 ml = __ldcg(src + 16);
+                        const float wq = ex2f(ml.x - m_all);
+                        l_run = fmaf(ml.y, wq, l_run);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 a = __ldcg(src + i / 4), b = __ldcg(src + 8 + i / 4);
+                            o[i] = __float_as_uint(fmaf(a.x, wq, __uint_as_float(o[i])));
+                            o[i + 1] = __float_as_uint(fmaf(a.y, wq, __uint_as_float(o[i + 1])));
+                            o[i + 2] = __float_as_uint(fmaf(a.z, wq, __uint_as_float(o[i + 2])));
+                            o[i + 3] = __float_as_uint(fmaf(a.w, wq, __uint_as_float(o[i + 3])));
+                            o2[i] = __float_as_uint(fmaf(b.x, wq, __uint_as_float(o2[i])));
+                            o2[i + 1] = __float_as_uint(fmaf(b.y, wq, __uint_as_float(o2[i + 1])));
+                            o2[i + 2] = __float_as_uint(fmaf(b.z, wq, __uint_as_float(o2[i + 2])));
+                            o2[i + 3] = __float_as_uint(fmaf(b.w, wq, __uint_as_float(o2[i + 3])));
+                        }
+                    }
+                }
+            }
+            const float inv_l = 1.0f / l_run;
+            if (write_out && row < seg_end) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)row * p.d_model + head * HD);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    dst[i / 8] = make_uint4(pack_half2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l),
+                                            pack_half2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l));
+                    dst[4 + i / 8] = make_uint4(pack_half2(__uint_as_float(o2[i]) * inv_l, __uint_as_float(o2[i + 1]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 2]) * inv_l, __uint_as_float(o2[i + 3]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 4]) * inv_l, __uint_as_float(o2[i + 5]) * inv_l),
+                                                pack_half2(__uint_as_float(o2[i + 6]) * inv_l, __uint_as_float(o2[i + 7]) * inv_l));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 // ======================================================================================= persistent (stream-K) variant
 // Same per-block pipeline as fmha_kernel<2>, but ONE CTA per SM walks a list of items (FmhaSchedule::cta_ptr): barriers, TMEM and the
 // K/V ring are set up once and keep running across items.  Phase bookkeeping is by running counters instead of the block index:
@@ -829,10 +1139,11 @@ static int launch_t(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_items, c
     return RAP_OK;
 }
 
+int g_fmha_rows_override = 0;                         // micro entry points / tests: force 128 / 256 / 384 query rows per CTA
 int fmha_rows_per_cta() {
     static int rows = 0;
-    if (!rows) { const char* e = getenv("RAP_FMHA_NT"); rows = (e && atoi(e) == 1) ? 128 : 256; }
-    return rows;
+    if (!rows) { const char* e = getenv("RAP_FMHA_NT"); const int nt = e ? atoi(e) : 2; rows = nt == 1 ? 128 : nt == 3 ? 384 : 256; }
+    return g_fmha_rows_override > 0 ? g_fmha_rows_override : rows;
 }
 
 size_t FmhaSchedule::workspace_floats() const { return (size_t)n_slots * max_pieces * fmha_rows_per_cta() * kWsRow; }
@@ -1083,8 +1394,20 @@ FmhaSchedule build_fmha_schedule_auto(const std::vector<int>& cu, int heads, boo
     return fmha_persistent_enabled() ? build_fmha_schedule_persistent(cu, heads, 0, force_split) : build_fmha_schedule(cu, heads, force_split);
 }
 
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaStream_t st) {
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaStream_t st, const CUtensorMap* tm_kv64) {
     RAP_REQUIRE(n_ctas > 0 && a.items && a.d_model % HD == 0, "fmha: bad args (ctas=%d d=%d)", n_ctas, a.d_model);
+    if (!a.cta_ptr && fmha_rows_per_cta() == 384) {        // three query tiles, 64-key blocks
+        RAP_REQUIRE(tm_kv64, "fmha: the 3-tile kernel needs the 64-row K/V tensor map");
+        static bool configured3 = false;
+        if (!configured3) {
+            RAP_CUDA(cudaFuncSetAttribute(fmha3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::SMEM_BYTES));
+            configured3 = true;
+        }
+        ProfScope _ps(KC_FMHA, st);
+        RAP_CUDA(launch_pdl(fmha3_kernel, dim3(n_ctas), dim3(k3::kThreads), k3::SMEM_BYTES, st, tm_qkv, *tm_kv64, a));
+        note_launch();
+        return RAP_OK;
+    }
     if (a.cta_ptr) {
         static bool configured = false;
         if (!configured) {

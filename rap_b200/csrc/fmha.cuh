@@ -59,9 +59,12 @@ struct FmhaArgs {
 };
 
 // tm_qkv: tensor map over the [T, 3*d_model] fp16 qkv buffer, box = 128 rows x 64 cols, SWIZZLE_128B.
-// Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM) -- schedules must match.
+// Query rows per CTA (256: two tiles ping-ponged by one UMMA warp; 128: one tile, two CTAs per SM; 384: three tiles on 64-key blocks) --
+// schedules must match.
 int fmha_rows_per_cta();
 // n_ctas = FmhaSchedule::n_ctas(): the grid (number of items for the one-item-per-CTA kernel).
-int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_ctas, cudaStream_t st);
+// tm_kv64: the same buffer with 64-row boxes -- needed by the three-tile kernel (RAP_FMHA_NT=3: 384 query rows per CTA, 64-key blocks).
+int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& args, int n_ctas, cudaStream_t st, const CUtensorMap* tm_kv64 = nullptr);
+extern int g_fmha_rows_override;            // micro entry points / tests: force the query rows per CTA (0 = RAP_FMHA_NT)
 
 }  // namespace rap

@@ -136,7 +136,8 @@ def test_gemm_geglu(rap):
 # force=3: the kernel the product launches (one item per CTA), 2: with its last wave force-split; 0 / 1: the opt-in persistent stream-K kernel
 # (wave-major schedule; 1 = a tiny per-CTA share, so small inputs are cut into pieces and recombined too); 4 / 5: the same with one
 # contiguous range per CTA
-@pytest.mark.parametrize("force", [3, 2, 7, 6, 0, 1, 4, 5])      # 6 / 7: as 2 / 3 with one UMMA-issuing warp per query tile
+@pytest.mark.parametrize("force", [3, 2, 7, 6, 8, 9, 0, 1, 4, 5])      # 6 / 7: as 2 / 3 with one UMMA-issuing warp per query tile; 8 / 9: the
+# three-tile kernel (384 query rows per CTA on 64-key blocks), plain / last wave force-split
 @pytest.mark.parametrize("lens", [[128], [200, 136, 72], [4096], [1, 127, 129, 300], [1024, 1024, 2048], [512, 512], [2000, 1500],
                                   [4096, 4096], [8192], [16384]])
 def test_fmha_varlen(rap, lens, force):
@@ -157,7 +158,7 @@ def test_fmha_varlen(rap, lens, force):
     assert err < 1e-2, f"max err {err}"
 
 
-@pytest.mark.parametrize("force", [2, 1])
+@pytest.mark.parametrize("force", [2, 1, 9])
 def test_fmha_lazy_reference_overflow_path(rap, force):
     """Adversarial scores for the lazy reference exponent: the first K/V block scores ~0, later blocks reach 2^40 times more, so
     the stale-reference pass must detect fp16 overflow of P and take the re-reference + O/l rescale path (several times)."""
