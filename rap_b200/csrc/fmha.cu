@@ -419,7 +419,7 @@ constexpr int kThreads = 64 + NT * 128;
 constexpr uint32_t TM_TILE3 = 160, TM_S3 = 0, TM_P3 = 64, TM_O3 = 96;
 }  // namespace k3
 
-__global__ void __launch_bounds__(k3::kThreads, 1)
+__global__ void __launch_bounds__(k3::kThreads + 64, 1)
 fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const FmhaArgs p) {
     using namespace k3;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -431,6 +431,9 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const int kv_begin = item.kv_lo, kv_end = item.kv_hi;
     const int n_kv = (kv_end - kv_begin + BK3 - 1) / BK3;
     const int nt = min(NT, (seg_end - q0 + BQ - 1) / BQ);           // query tiles with rows inside the segment
+    // mma3 (launch with 512 threads): one UMMA-issuing warp per query tile (warps 1, 14, 15) instead of one warp walking the tiles in a fixed
+    // order -- with three tiles the fixed order keeps them in lockstep.
+    const bool mma3 = blockDim.x > (unsigned)kThreads;
 
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t q_full = bar;
@@ -449,7 +452,7 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
         mbar_init(q_full, 1);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), mma3 ? nt : 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), mma3 ? nt : 1); }
         for (int t = 0; t < NT; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4); }
         mbar_fence_init();
     }
@@ -476,8 +479,9 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             if (leader) { mbar_expect_tx(v_full(s), KV_TILE); tma_load_2d(sbase + OFF_V + s * KV_TILE, &tm_kv, v_full(s), col_v, row); }
             if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp >= 14) {
         const bool leader = elect_one();
+        const int t_lo = mma3 ? (warp == 1 ? 0 : warp - 13) : 0, t_hi = mma3 ? min(t_lo + 1, nt) : (warp == 1 ? nt : 0);
         constexpr uint32_t idesc_qk = umma_idesc_f16(BQ, BK3, false, false);   // A = Q (K-major), B = K (K-major), N = 64 keys
         constexpr uint32_t idesc_pv = umma_idesc_f16(BQ, HD, false, true);     // A = P (TMEM), B = V (MN-major), N = 64 dims
         auto issue_qk = [&](int t, int s) {
@@ -489,10 +493,11 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 umma_commit(s_full(t));
             }
         };
+        if (t_lo < t_hi) {
         mbar_wait(q_full, 0, 0x50);
         mbar_wait(k_full(0), 0, 0x51);
         tc_fence_after();
-        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
+        for (int t = t_lo; t < t_hi; ++t) issue_qk(t, 0);
         if (leader) umma_commit(k_empty(0));
         int s = 0; uint32_t ph = 0;
         for (int j = 0; j < n_kv; ++j) {
@@ -500,15 +505,15 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             const uint32_t ph1 = (s + 1 == STAGES) ? ph ^ 1 : ph;
             const bool more = j + 1 < n_kv;
             const uint64_t dv0 = umma_desc_sw128(sbase + OFF_V + s * KV_TILE, 1024);
-            for (int t = 0; t < nt; ++t) {
+            for (int t = t_lo; t < t_hi; ++t) {
                 if (more) {
-                    if (t == 0) mbar_wait(k_full(s1), ph1, 0x53);
+                    if (t == t_lo) mbar_wait(k_full(s1), ph1, 0x53);
                     mbar_wait(s_free(t), j & 1, 0x55);
                     tc_fence_after();
                     issue_qk(t, s1);
-                    if (t == nt - 1 && leader) umma_commit(k_empty(s1));
+                    if (t == t_hi - 1 && leader) umma_commit(k_empty(s1));
                 }
-                if (t == 0) mbar_wait(v_full(s), ph, 0x54);
+                if (t == t_lo) mbar_wait(v_full(s), ph, 0x54);
                 mbar_wait(p_full(t), j & 1, 0x52);
                 tc_fence_after();
                 if (leader) {
@@ -516,10 +521,11 @@ fmha3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                     for (int k = 0; k < BK3 / 16; ++k)       // A = P from TMEM: 8 columns per K=16 step; V: +2 KB per 16 keys (encoded >> 4)
                         umma_f16_ts(tmem + t * TM_TILE3 + TM_O3, tmem + t * TM_TILE3 + TM_P3 + k * 8, dv0 + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
                     umma_commit(pv_done(t));
-                    if (t == nt - 1) umma_commit(v_empty(s));
+                    if (t == t_hi - 1) umma_commit(v_empty(s));
                 }
             }
             s = s1; ph = ph1;
+        }
         }
     } else {
         const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
@@ -1404,7 +1410,9 @@ int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaSt
             configured3 = true;
         }
         ProfScope _ps(KC_FMHA, st);
-        RAP_CUDA(launch_pdl(fmha3_kernel, dim3(n_ctas), dim3(k3::kThreads), k3::SMEM_BYTES, st, tm_qkv, *tm_kv64, a));
+        static int mma3 = -1;                            // RAP_FMHA_MMA3=0: one UMMA warp walks the three tiles in a fixed order
+        if (mma3 < 0) { const char* e = getenv("RAP_FMHA_MMA3"); mma3 = (e && atoi(e) == 0) ? 0 : 1; }
+        RAP_CUDA(launch_pdl(fmha3_kernel, dim3(n_ctas), dim3(k3::kThreads + (mma3 ? 64 : 0)), k3::SMEM_BYTES, st, tm_qkv, *tm_kv64, a));
         note_launch();
         return RAP_OK;
     }
