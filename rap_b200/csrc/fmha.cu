@@ -326,77 +326,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaArgs p) {
             tmem_ld32(tm_o + 32, o2);
             tmem_ld_wait();
             bool write_out = true;
-            if (item.slot >= 0 && p.flag_combine) {
-                // Split unit, wait-free protocol (default): pieces are numbered in launch order (the big piece of a unit is dispatched before its
-                // small ones), so the LAST piece is the combiner: every earlier piece stores its un-normalised row (O, reference exponent,
-                // row sum) and, behind a fence, a per-row flag carrying this launch's generation number, and is done -- no CTA barrier, no
-                // atomic; the last piece polls the flags of its own row in the earlier pieces (CTAs with a lower blockIdx: dispatched
-                // before it, so the bounded wait cannot deadlock), merges them in piece order with its own row straight from registers
-                // (the same sequence of FMAs as the handshake protocol below: bit-identical results) and clears the flags it consumed.
-                const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
-                float* unit_ws = p.ws + (size_t)item.slot * p.ws_pieces * (NT * BQ) * kWsRow;
-                const size_t piece_stride = (size_t)(NT * BQ) * kWsRow;
-                float* my_row = unit_ws + (size_t)(t * BQ + r) * kWsRow;
-                if (piece != n_pieces - 1) {
-                    float4* mine = reinterpret_cast<float4*>(my_row + piece * piece_stride);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        __stcg(mine + i / 4, make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3])));
-                        __stcg(mine + 8 + i / 4, make_float4(__uint_as_float(o2[i]), __uint_as_float(o2[i + 1]), __uint_as_float(o2[i + 2]), __uint_as_float(o2[i + 3])));
-                    }
-                    __stcg(reinterpret_cast<float2*>(mine + 16), make_float2(m_run, l_run));
-                    __threadfence();
-                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(mine + 16) + 2), "r"((uint32_t)p.gen) : "memory");
-                    write_out = false;
-                } else {
-                    const long long t_spin = clock64();
-                    float m_all = -INFINITY;
-                    for (int q = 0; q < n_pieces - 1; ++q) {
-                        const uint32_t* flag = reinterpret_cast<const uint32_t*>(my_row + q * piece_stride + 66);
-                        uint32_t seen, spins = 0;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-                            if (seen != (uint32_t)p.gen && (++spins & 0x3ff) == 0 && clock64() - t_spin > 8000000000ll) {
-                                atomicCAS(&g_dev_error, 0u, 0x72u | (blockIdx.x << 8));
-                                __threadfence_system();
-                                __trap();
-                            }
-                        } while (seen != (uint32_t)p.gen);
-                        m_all = fmaxf(m_all, __ldcg(my_row + q * piece_stride + 64));
-                    }
-                    m_all = fmaxf(m_all, m_run);
-                    const float w_own = ex2f(m_run - m_all), l_own = l_run;
-                    uint32_t own[32], own2[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { own[i] = o[i]; own2[i] = o2[i]; o[i] = 0u; o2[i] = 0u; }
-                    l_run = 0.f;
-                    for (int q = 0; q < n_pieces - 1; ++q) {
-                        const float4* src = reinterpret_cast<const float4*>(my_row + q * piece_stride);
-                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(src + 16));
-                        const float wq = ex2f(ml.x - m_all);
-                        l_run = fmaf(ml.y, wq, l_run);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 a = __ldcg(src + i / 4), b = __ldcg(src + 8 + i / 4);
-                            o[i] = __float_as_uint(fmaf(a.x, wq, __uint_as_float(o[i])));
-                            o[i + 1] = __float_as_uint(fmaf(a.y, wq, __uint_as_float(o[i + 1])));
-                            o[i + 2] = __float_as_uint(fmaf(a.z, wq, __uint_as_float(o[i + 2])));
-                            o[i + 3] = __float_as_uint(fmaf(a.w, wq, __uint_as_float(o[i + 3])));
-                            o2[i] = __float_as_uint(fmaf(b.x, wq, __uint_as_float(o2[i])));
-                            o2[i + 1] = __float_as_uint(fmaf(b.y, wq, __uint_as_float(o2[i + 1])));
-                            o2[i + 2] = __float_as_uint(fmaf(b.z, wq, __uint_as_float(o2[i + 2])));
-                            o2[i + 3] = __float_as_uint(fmaf(b.w, wq, __uint_as_float(o2[i + 3])));
-                        }
-                        *reinterpret_cast<volatile uint32_t*>(const_cast<float*>(my_row + q * piece_stride + 66)) = 0u;   // consumed
-                    }
-                    l_run = fmaf(l_own, w_own, l_run);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        o[i] = __float_as_uint(fmaf(__uint_as_float(own[i]), w_own, __uint_as_float(o[i])));
-                        o2[i] = __float_as_uint(fmaf(__uint_as_float(own2[i]), w_own, __uint_as_float(o2[i])));
-                    }
-                }
-            } else if (item.slot >= 0) {
+            if (item.slot >= 0) {
                 // Split unit: publish this piece's un-normalised row (O, reference exponent, row sum); the piece that arrives last
                 // re-references all of them to the largest exponent, adds them up and writes the output.
                 const int piece = item.piece & 0xff, n_pieces = item.piece >> 8;
@@ -1501,10 +1431,7 @@ int launch_fmha(const CUtensorMap& tm_qkv, const FmhaArgs& a, int n_ctas, cudaSt
     if (early < 0) { const char* e = getenv("RAP_FMHA_EARLY"); early = (e && atoi(e) == 1) ? 1 : 0; }
     static int mma2 = -1;                                // RAP_FMHA_MMA2: one UMMA-issuing warp per query tile (A/B)
     if (mma2 < 0) { const char* e = getenv("RAP_FMHA_MMA2"); mma2 = e ? (atoi(e) != 0 ? 1 : 0) : 0; }
-    static int flagc = -1;                               // RAP_FMHA_COMBINE=0: the handshake protocol (partials + fence + CTA barrier + atomic) for cut units
-    if (flagc < 0) { const char* e = getenv("RAP_FMHA_COMBINE"); flagc = (e && atoi(e) == 0) ? 0 : 1; }
     FmhaArgs b = a;
-    b.flag_combine = (flagc && a.gen != 0) ? 1 : 0;
     b.mma2 = (a.mma2 || mma2) ? 1 : 0;
     b.early_release = early && a.score_bound;
     return fmha_rows_per_cta() == 128 ? launch_t<1>(tm_qkv, b, n_ctas, st) : launch_t<2>(tm_qkv, b, n_ctas, st);

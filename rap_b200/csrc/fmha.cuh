@@ -48,8 +48,6 @@ struct FmhaArgs {
     int d_model;         // heads * 64; qkv rows are [q | k | v], each d_model wide
     float scale_log2;    // log2(e) / sqrt(head_dim)
     const float* score_bound;  // [heads] upper bound of |score * scale_log2| (from the qk-norm gammas), or null = unknown
-    int flag_combine;    // one-item-per-CTA kernel: cut units are merged by their last piece from per-row flagged partial rows (needs gen != 0; set by
-                         // launch_fmha, RAP_FMHA_COMBINE=0 restores the barrier + atomic handshake)
     int mma2;            // one-item-per-CTA kernel: a second UMMA-issuing warp (warp 10) takes query tile 1 (set by launch_fmha from RAP_FMHA_MMA2)
     int early_release;   // hand S back before the exponentials when score_bound rules out the slow path (set by launch_fmha from RAP_FMHA_EARLY)
     float* ws;           // partial rows [slot][piece][rows_per_cta][68] (64 un-normalised outputs, reference exponent, row sum, pad), or null
