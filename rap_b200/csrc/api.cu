@@ -871,6 +871,7 @@ struct DevSchedule {
             RAP_CUDA(cudaMemcpy(cta_ptr, sch.cta_ptr.data(), 4 * sch.cta_ptr.size(), cudaMemcpyHostToDevice));
         }
         RAP_CUDA(cudaMalloc(&ws, 4 * sch.workspace_floats() + 16));
+        RAP_CUDA(cudaMemset(ws, 0, 4 * sch.workspace_floats() + 16));             // the persistent kernel's "published" flags live in here
         RAP_CUDA(cudaMalloc(&counters, 4 * (size_t)sch.n_slots + 4));
         RAP_CUDA(cudaMemset(counters, 0, 4 * (size_t)sch.n_slots + 4));
         return RAP_OK;
