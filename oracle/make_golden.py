@@ -33,6 +33,7 @@ BIG_CASES = {
     "cfg3_4x4096_s3_rigid": (12, 1, 4, 4096, 3, True, 4, (0, 2)),                # configs[2] shape, rigidity forcing on (RAP_inference.yaml:58)
     "cfg1_2x512_s5_p512": (12, 1, 2, 512, 5, True, 512, (0, 4)),                 # max_parts: 512 padding (RAP_inference.yaml:33)
     "small_L2_s70": (2, 2, 2, [96, 64], 70, False, 3, (0, 63, 64, 69)),          # more than 64 flow steps (timestep table beyond one block)
+    "cfg5_2x16384_s1": (12, 1, 2, 16384, 1, False, 2, (0,)),                     # configs[4] size: 16384 pts/view (256 key blocks per scene), one step + one forward
 }
 
 

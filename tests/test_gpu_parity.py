@@ -47,7 +47,8 @@ def _stats(a, b):
     return d.max().item(), d.mean().item()
 
 
-@pytest.mark.parametrize("name", ["ragged_b2_v3_L2_s3_rigid", "cfg1_2x512_s5", "cfg2_2x4096_s20", "cfg3_4x4096_s3_rigid", "cfg1_2x512_s5_p512"])
+@pytest.mark.parametrize("name", ["ragged_b2_v3_L2_s3_rigid", "cfg1_2x512_s5", "cfg2_2x4096_s20", "cfg3_4x4096_s3_rigid", "cfg1_2x512_s5_p512",
+                                  "cfg5_2x16384_s1"])
 def test_forward_vs_reference_golden(golden_dir, name):
     L, B, V, N, _, _, P, _ = case_params(name)
     b = make_batch(B, V, N, max_parts=P).to("cuda")
