@@ -54,7 +54,12 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // ((128 + 256) rows x 128 B per 128x256x64 step at ~42 B/clk/SM of L2 bandwidth when every SM streams, against 512 tensor-pipe cycles), see
 // DESIGN.md.  A stage is free again when BOTH CTAs have consumed it: the empty barriers count two arrivals and every UMMA commit arrives on
 // the barrier of both CTAs (tcgen05.commit ... .multicast::cluster).
-template <int BN, int EPI, bool MC>
+// TWO (2-CTA UMMA, `cta_group::2`): the same pair of vertically adjacent tiles runs as ONE 256x256 UMMA.  Each CTA keeps its own A tile
+// and only ITS half of the B tile in shared memory (32 KB per stage instead of 48: the K loop of these GEMMs is bound by what an SM can
+// ingest); the even CTA of the pair issues the MMAs for both, each CTA's accumulator rows land in its own TMEM, and the epilogues are
+// untouched.  Loads of both CTAs are counted on the even CTA's stage barrier, stage / accumulator hand-backs are multicast commits and one
+// remote arrive per epilogue warp.
+template <int BN, int EPI, bool MC, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
     using C = Cfg<BN>;
@@ -75,10 +80,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_blocks = p.K / BK;
     // Work units: tiles (one CTA each), or with MC pairs of vertically adjacent tiles (one cluster each; an odd last row of tiles gets a
     // dummy partner whose loads are zero-filled and whose stores are masked).  first_tile / tile_step walk this CTA's units; unit -> (m0, n0).
-    const uint32_t crank = MC ? cluster_ctarank() : 0u;
-    const int num_tiles = MC ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
-    const int first_tile = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    auto tile_m0 = [&](int tile) { return (MC ? 2 * (tile / n_tiles) + (int)crank : tile / n_tiles) * BM; };
+    static_assert(!(MC && TWO) && (!TWO || BN == 256), "pair modes: multicast OR 2-CTA UMMA, the latter on 256-wide tiles");
+    constexpr bool PAIR = MC || TWO;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const int num_tiles = PAIR ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m0 = [&](int tile) { return (PAIR ? 2 * (tile / n_tiles) + (int)crank : tile / n_tiles) * BM; };
     auto tile_n0 = [&](int tile) { return (tile % n_tiles) * BN; };
     constexpr int B_BOXES = BN / 128 > 0 ? BN / 128 : 1;      // the B tensor map has 128-row boxes (BN = 256: two per stage)
     constexpr int B_BOX_ROWS = BN < 128 ? BN : 128;
@@ -88,17 +95,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }   // TWO: both CTAs' epilogue warps
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    if (warp == 1) { if constexpr (TWO) tmem_alloc_2cta<C::TMEM_COLS>(tmem_slot); else tmem_alloc<C::TMEM_COLS>(tmem_slot); }
     if (EPI == EPI_QKV) {
         for (int i = threadIdx.x; i < 2 * 8 * 64; i += kThreads) gamma_s[i] = p.gamma[i];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if constexpr (MC) { cluster_arrive(); cluster_wait(); }     // the partner's barriers exist before anything is multicast at them
+    if constexpr (PAIR) { cluster_arrive(); cluster_wait(); }   // the partner's barriers exist before anything is multicast at them
     const uint32_t tmem_base = *tmem_slot_gen;
     // Programmatic dependent launch: only the A operand, the residual and the outputs depend on the previous kernel.  The weight
     // (B) tiles of the first pipeline stages are requested BEFORE griddepcontrol.wait, so their fetch latency hides under the
@@ -111,9 +118,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------------------------------------------------------------ TMA producer (warp converged, one elected lane issues)
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
-        const int pre = (first_tile < num_tiles) ? min(C::STAGES, k_blocks) : 0;   // stages whose B tile is in flight before the wait
+        const int pre = (!TWO && first_tile < num_tiles) ? min(C::STAGES, k_blocks) : 0;   // stages whose B tile is in flight before the wait
         auto load_b = [&](uint32_t sb, uint32_t bar, int kcol, int n0) {            // this CTA's share of the B tile of one stage
-            if constexpr (MC) {
+            if constexpr (TWO) {
+                tma_load_2d_2cta(sb, &tmB, bar, kcol, n0 + (int)crank * B_BOX_ROWS);
+            } else if constexpr (MC) {
                 tma_load_2d_mc(sb + crank * B_BOX_BYTES, &tmB, bar, kcol, n0 + (int)crank * B_BOX_ROWS, (uint16_t)3);
             } else {
 #pragma unroll
@@ -137,6 +146,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (!b_done) mbar_wait(empty_bar(stage), phase ^ 1, 0x11);
                 if (leader) {
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    if constexpr (TWO) {
+                        // the even CTA's barrier counts the bytes of both CTAs: 2 x (A tile + half a B tile)
+                        const uint32_t bar0 = dsmem_addr(full_bar(stage), 0u);
+                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * (A_STAGE_BYTES + B_BOX_BYTES));
+                        tma_load_2d_2cta(sa, &tmA, bar0, kb * BK, m0);
+                        load_b(sa + A_STAGE_BYTES, bar0, kb * BK, n0);
+                    } else {
                     if (!b_done) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     int a_col = kb * BK, a_row = m0;
                     if (p.conv_pitch) {                          // implicit 3x3 convolution: shifted box of the halo-padded activation map
@@ -146,6 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     tma_load_2d(sa, &tmA, full_bar(stage), a_col, a_row);
                     if (!b_done) load_b(sa + A_STAGE_BYTES, full_bar(stage), kb * BK, n0);
+                    }
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -155,9 +172,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ------------------------------------------------------------ UMMA issuer (warp converged: descriptors stay warp-uniform)
         const bool leader = elect_one();
-        constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+        constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * BM : BM, BN, false, false);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {
+        for (int tile = (TWO && crank != 0) ? num_tiles : first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {   // TWO: the even CTA issues for the pair
             GEMM_TS(2);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1, 0x21);
             tc_fence_after();
@@ -170,14 +187,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint64_t da = umma_desc_sw128(sa, 1024), db = umma_desc_sw128(sa + A_STAGE_BYTES, 1024);
                 if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)   // +32 bytes (encoded +2) per K=16 step inside the swizzle row
-                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)3);   // both CTAs of the pair learn that this one is done with the stage
+                    for (int k = 0; k < BK / 16; ++k) { // +32 bytes (encoded +2) per K=16 step inside the swizzle row
+                        if constexpr (TWO) umma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if constexpr (TWO) umma_commit_2cta(empty_bar(stage), (uint16_t)3);     // the stage is free in BOTH CTAs when the pair's MMAs retire
+                    else if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)3);   // both CTAs of the pair learn that this one is done with the stage
                     else umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
-            if (leader) umma_commit(tfull_bar(acc));     // accumulator ready for the epilogue
+            if (leader) { if constexpr (TWO) umma_commit_2cta(tfull_bar(acc), (uint16_t)3); else umma_commit(tfull_bar(acc)); }   // accumulator ready for the epilogue(s)
             GEMM_TS(4);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -464,31 +484,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (dbg_w) GEMM_TS(7);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (TWO && crank != 0) mbar_arrive_cluster(dsmem_addr(tempty_bar(acc), 0u));   // the even CTA's UMMA warp waits for both epilogues
+                else mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (MC) { cluster_arrive(); cluster_wait(); }     // no CTA leaves while its partner may still multicast into it / arrive on its barriers
-    if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) { cluster_arrive(); cluster_wait(); }   // no CTA leaves while its partner may still multicast into it / arrive on its barriers
+    if (warp == 1) { if constexpr (TWO) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base); }
 }
 
-template <int BN, int EPI, bool MC = false>
+template <int BN, int EPI, bool MC = false, bool TWO = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN;
     ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
-    if constexpr (MC) {
+    if constexpr (MC || TWO) {
         const int pairs = ((m_tiles + 1) / 2) * n_tiles;
         const int clusters = std::min(pairs, num_sms() / 2);
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, true>, dim3(2 * clusters), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, MC, TWO>, dim3(2 * clusters), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
         note_launch();
         return RAP_OK;
     }
@@ -511,6 +534,12 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
 // 99.59 / 99.66 / 99.50 ms per pair with it, 99.46 / 99.56 / 99.54 without; in isolation 2-10 % SLOWER (QKV 16.6 vs 15.9 us, out-proj 10.3 vs
 // 9.4).  It removes 27 % of the L2 reads (ncu lts__throughput 37.9 % -> 27.6 % on the GEGLU GEMM) but not one byte of what each SM has to
 // ingest, which is what bounds the K loop, and it couples the two CTAs' pipelines.  Hence off by default.
+// RAP_GEMM_2CTA=1: pairs of CTAs run 256x256 UMMAs with `cta_group::2` (each SM ingests half of the weight tile).
+bool gemm_two_cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_GEMM_2CTA"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
+}
 bool gemm_multicast() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RAP_GEMM_MC"); v = (e && atoi(e) == 1) ? 1 : 0; }
@@ -523,6 +552,15 @@ int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& 
     RAP_REQUIRE(a.M > 0 && a.N % BN == 0 && a.K % BK == 0 && a.K >= BK, "gemm: bad shape M=%d N=%d K=%d BN=%d", a.M, a.N, a.K, BN);
     if (BN == 256) {
         const bool mc = (a.mc == 1 || (a.mc == 0 && gemm_multicast())) && !a.conv_pitch && a.M > BM;      // a single row of tiles has nothing to share
+        const bool two = (a.mc == 3 || (a.mc == 0 && gemm_two_cta())) && !a.conv_pitch && a.M > BM;
+        if (two) {
+            switch (epi) {
+                case EPI_F32: return launch_t<256, EPI_F32, false, true>(tmA, tmB, a, st);
+                case EPI_QKV: return launch_t<256, EPI_QKV, false, true>(tmA, tmB, a, st);
+                case EPI_GEGLU: return launch_t<256, EPI_GEGLU, false, true>(tmA, tmB, a, st);
+                default: break;
+            }
+        }
         switch (epi) {
             case EPI_F32: return mc ? launch_t<256, EPI_F32, true>(tmA, tmB, a, st) : launch_t<256, EPI_F32>(tmA, tmB, a, st);
             case EPI_QKV: return mc ? launch_t<256, EPI_QKV, true>(tmA, tmB, a, st) : launch_t<256, EPI_QKV>(tmA, tmB, a, st);

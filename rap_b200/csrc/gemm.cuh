@@ -31,7 +31,7 @@ struct GemmArgs {
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
-    int mc;                   // B-tile multicast over 2-CTA clusters: 0 = as RAP_GEMM_MC says (default off), 1 = on, 2 = off
+    int mc;                   // pair modes: 0 = as RAP_GEMM_MC / RAP_GEMM_2CTA say (default off), 1 = B-tile multicast, 2 = plain, 3 = 2-CTA UMMA
     // EPI_F32_LN: modulation rows ln_mul / ln_add are selected per token, sel(row) = ln_row_of_tok[row] * ln_row_stride (AdaLN table row of the
     // token's scene; stride 0 + an all-zero index vector for the plain affine LayerNorm in front of the feed-forward block)
     const float* ln_mul;

@@ -121,6 +121,40 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {    // same warp t
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
+// cta_group::2 variants: the two CTAs of a cluster pair act as one 256-row UMMA.  Allocation / deallocation are issued by the same warp of
+// BOTH CTAs (same shared-memory slot offset); loads signal the barrier of the pair's even CTA; the MMA is issued by the even CTA only.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose completion bytes are counted on the mbarrier at cluster address `bar_cluster`
+// (the even CTA's barrier of the stage).
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem: 128 rows in each CTA] * B[smem: N/2 rows in each CTA]; M = 256.  Issued by ONE thread of the even CTA.
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// Arrive on the mbarrier at this offset in the CTAs of cta_mask when all previously issued cta_group::2 UMMAs have completed.
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// Arrive on an mbarrier of another CTA of the cluster (address from dsmem_addr).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 // ------------------------------------------------------------------ UMMA
 // Shared-memory matrix descriptor, 128-byte swizzle, tile rows of exactly 128 bytes
 // (64 fp16).  K-major operand: rows = M/N index, 8-row groups `sbo_bytes` apart.

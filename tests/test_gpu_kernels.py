@@ -77,19 +77,21 @@ def test_gemm_f32_layernorm_epilogue(rap, M, K, in_place, per_row):
     assert err < 2e-2, f"max err {err}"
 
 
+@pytest.mark.parametrize("mode", [0x100, 0x300])
 @pytest.mark.parametrize("M", [8192, 257, 1000])
-def test_gemm_multicast_cluster_variant(rap, M):
-    """The opt-in 2-CTA-cluster GEMM (weight tile fetched half by each CTA and multicast into both, two-arrival stage barriers):
-    f32 residual, QKV + RMS-norm and GEGLU epilogues, even and odd numbers of 128-row tiles (257 -> a dummy partner tile)."""
+def test_gemm_multicast_cluster_variant(rap, M, mode):
+    """The opt-in pair GEMMs on 2-CTA clusters -- 0x100: weight tile fetched half by each CTA and multicast into both (two-arrival stage
+    barriers); 0x300: `cta_group::2` UMMA, one 256x256 MMA per pair with each CTA holding half of the weight tile -- f32 residual and QKV +
+    RMS-norm epilogues, even and odd numbers of 128-row tiles (257 -> a dummy partner tile)."""
     g = torch.Generator("cuda").manual_seed(M)
     A = torch.randn(M, 512, device="cuda", generator=g).half()
     W = (torch.randn(512, 512, device="cuda", generator=g) / 22.6).half()
     bias, add = torch.randn(512, device="cuda", generator=g), torch.randn(M, 512, device="cuda", generator=g)
-    out32, _ = _gemm(rap, 0 | 0x100, 256, A, W, bias, add)
+    out32, _ = _gemm(rap, 0 | mode, 256, A, W, bias, add)
     assert (out32 - (A.float() @ W.float().t() + bias + add)).abs().max().item() < 2e-3
     Wq = (torch.randn(1536, 512, device="cuda", generator=g) / 22).half()
     gamma = 1 + 0.1 * torch.randn(2, 8, 64, device="cuda", generator=g)
-    _, out16 = _gemm(rap, 2 | 0x100, 256, A, Wq, gamma=gamma)
+    _, out16 = _gemm(rap, 2 | mode, 256, A, Wq, gamma=gamma)
     qkv = (A.float() @ Wq.float().t()).view(M, 3, 8, 64)
     ref = torch.stack([F.normalize(qkv[:, 0], dim=-1) * gamma[0] * 8, F.normalize(qkv[:, 1], dim=-1) * gamma[1] * 8, qkv[:, 2]], 1).reshape(M, 1536)
     assert (out16.float() - ref).abs().max().item() < 2e-2
