@@ -23,10 +23,13 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int STG_ROW_BYTES = 144;
 constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;
 
-template <int BN> struct Cfg {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+// TWO (2-CTA UMMA): a CTA holds only half of the 256-row B tile per stage (32 KB stages), so five of them fit where three 48 KB ones did:
+// 160 KB instead of 144 KB in flight for 2/3 of the bytes per K step (the K loop is bound by bytes in flight / TMA latency: 3 x 48 KB over
+// ~2 k cycles = 72 B/clk per SM, against 96 B/clk that 512-cycle K steps would need).
+template <int BN, bool TWO = false> struct Cfg {
+    static constexpr int B_STAGE_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 3 : 5;
+    static constexpr int STAGES = TWO ? 5 : (BN == 256) ? 3 : 5;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
     static constexpr int GAMMA_BYTES = 4096;
@@ -62,7 +65,7 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 template <int BN, int EPI, bool MC, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, TWO>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -149,7 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if constexpr (TWO) {
                         // the even CTA's barrier counts the bytes of both CTAs: 2 x (A tile + half a B tile)
                         const uint32_t bar0 = dsmem_addr(full_bar(stage), 0u);
-                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * (A_STAGE_BYTES + B_BOX_BYTES));
+                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
                         tma_load_2d_2cta(sa, &tmA, bar0, kb * BK, m0);
                         load_b(sa + A_STAGE_BYTES, bar0, kb * BK, n0);
                     } else {
@@ -500,7 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int BN, int EPI, bool MC = false, bool TWO = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, TWO>;
     static bool configured = false;
     if (!configured) {
         RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
