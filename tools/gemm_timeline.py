@@ -29,3 +29,5 @@ run("outproj f32", 0, 256, 8192, 512, 512)
 run("ff2 f32", 0, 256, 8192, 512, 2048)
 run("outproj f32 bn128", 0, 128, 8192, 512, 512)
 run("ff2 f32 bn128", 0, 128, 8192, 512, 2048)
+run("qkv rmsnorm", 2, 256, 8192, 1536, 512)
+run("geglu", 3, 256, 8192, 4096, 512)
