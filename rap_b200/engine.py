@@ -250,9 +250,7 @@ class Registrar:
             pts.append(r.points); Rs.append(r.rotations); ts.append(r.translations)
         R_loc = torch.cat(Rs) if Rs else torch.zeros(0, P, 3, 3, device=dev)
         t_loc = torch.cat(ts) if ts else torch.zeros(0, P, 3, device=dev)
-        points = torch.cat(pts) if len(pts) != 1 else pts[0]
-        if not pts:
-            points = torch.zeros(0, 3, device=dev)
+        points = torch.zeros(0, 3, device=dev) if not pts else pts[0] if len(pts) == 1 else torch.cat(pts)   # (a rank may own no scene)
         main = torch.cuda.current_stream()
         if world == 1:
             poses, done = gather_poses(R_loc, t_loc), None
