@@ -707,6 +707,7 @@ int ensure_graph_buffers(rap_plan* pl, int num_steps) {
         RAP_CUDA(cudaMalloc(&pl->g_feat, sizeof(float) * (size_t)pl->T * D));
     }
     if (num_steps > pl->g_steps_cap) {           // trajectories grow with the step count: re-allocate and drop the graphs that point at the old ones
+        if (!pl->graphs.empty()) RAP_CUDA(cudaDeviceSynchronize());            // (a replay may still be running on them)
         for (auto& g : pl->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         pl->graphs.clear();
         cudaFree(pl->g_ep); cudaFree(pl->g_tr);
