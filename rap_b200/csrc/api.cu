@@ -69,6 +69,14 @@ bool ln_fused() {
     return v == 1;
 }
 
+// RAP_GEMM_RED=1: the in-place residual GEMMs (out-proj, FF2) leave through bulk tensor reductions (EPI_F32_RED) instead of reading the
+// residual into the SM and storing the sum.
+bool gemm_red() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_GEMM_RED"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RAP_NO_PDL"); v = (e && atoi(e) == 1) ? 0 : 1; }
@@ -116,6 +124,22 @@ int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint6
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RAP_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return RAP_OK;
+}
+
+int make_tmap_f32_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(RAP_ENODEV, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    RAP_REQUIRE(box_rows >= 1 && box_rows <= 256 && cols % 32 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride_elems % 4 == 0,
+                "tensor map: bad geometry rows=%llu cols=%llu box_rows=%u", (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RAP_ECUDA, "cuTensorMapEncodeTiled (fp32) failed with %d", (int)r);
     return RAP_OK;
 }
 
@@ -388,7 +412,7 @@ struct rap_plan {
     float *h = nullptr, *h_static = nullptr, *x_t = nullptr, *tbuf = nullptr;
     __half *x16 = nullptr, *attn16 = nullptr, *qkv = nullptr, *ffmid = nullptr, *a_s = nullptr, *a_x = nullptr, *hh16 = nullptr, *y1 = nullptr, *y2 = nullptr;
     float *ada_e0 = nullptr, *ada_e1 = nullptr, *ada_e2 = nullptr, *ada_tab = nullptr;
-    CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn, tm_qkv_attn64;
+    CUtensorMap tm_x16, tm_attn16, tm_ffmid, tm_as, tm_ax, tm_hh16, tm_y1, tm_qkv_attn, tm_qkv_attn64, tm_h32;
     const float* cond = nullptr;
     const uint8_t* anchor = nullptr;
     bool condition_set = false;
@@ -477,6 +501,7 @@ extern "C" int rap_plan_create(rap_plan_t** out, rap_dit_t* dit, int n_scenes, c
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_as, pl->a_s, T, 128, 128, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_ax, pl->a_x, T, 64, 64, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_hh16, pl->hh16, T, D, D, 128);
+    if (!rc) rc = make_tmap_f32_sw128(&pl->tm_h32, pl->h, T, D, D, 32);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_y1, pl->y1, T, D, D, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_qkv_attn, pl->qkv, T, 3 * D, 3 * D, 128);
     if (!rc) rc = make_tmap_f16_sw128(&pl->tm_qkv_attn64, pl->qkv, T, 3 * D, 3 * D, 64);
@@ -594,7 +619,12 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             ln_args(g, next_ln);
             return launch_gemm(EPI_F32_LN, 256, ta, tb, g, st);
         }
-        RAP_TRY(launch_gemm(EPI_F32, f32_bn(), ta, tb, g, st));
+        if (gemm_red() && g.addend == g.out32 && !g.out16 && !g.table && f32_bn() == 256) {
+            g.tm_out32 = &pl->tm_h32;
+            RAP_TRY(launch_gemm(EPI_F32_RED, 256, ta, tb, g, st));
+        } else {
+            RAP_TRY(launch_gemm(EPI_F32, f32_bn(), ta, tb, g, st));
+        }
         if (has_next) {
             GemmArgs t{};
             ln_args(t, next_ln);
@@ -827,6 +857,8 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     g.mc = (epi >> 8) & 3;                                       // test hook: epi | 0x100 forces the multicast variant, | 0x200 forbids it
     epi &= 0xff;
     g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
+    CUtensorMap tc;
+    if (epi == EPI_F32_RED) { RAP_TRY(make_tmap_f32_sw128(&tc, out32, M, N, N, 32)); g.tm_out32 = &tc; }
     return launch_gemm(static_cast<GemmEpi>(epi), bn, ta, tb, g, static_cast<cudaStream_t>(stream));
 }
 

@@ -41,6 +41,9 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // 2D fp16 row-major tensor map with a (box_rows x 64 cols) box and 128-byte swizzle.
 int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                         uint32_t box_rows);
+// 2D fp32 row-major tensor map with a (box_rows x 32 cols = 128 B) box and 128-byte swizzle (bulk stores / reductions of GEMM epilogues).
+int make_tmap_f32_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                        uint32_t box_rows);
 
 int num_sms();
 

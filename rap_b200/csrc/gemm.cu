@@ -35,7 +35,13 @@ template <int BN, bool TWO = false> struct Cfg {
     static constexpr int GAMMA_BYTES = 4096;
     static constexpr int STG_OFF = STAGES * STAGE_BYTES + BAR_BYTES + GAMMA_BYTES;
     static constexpr int SMEM_BYTES = STG_OFF + 8 * STG_WARP_BYTES + 1024 /*align slack*/;
+    // EPI_F32_RED: instead of the transposing staging rows, every epilogue warp owns two 32-row x 128-byte boxes in the TMA's 128-byte swizzle
+    // (1024-byte aligned), double-buffered against the bulk reductions that read them.
+    static constexpr int RED_BOX_BYTES = 32 * 128;
+    static constexpr int RED_OFF = (STG_OFF + 1023) & ~1023;
+    static constexpr int RED_SMEM_BYTES = RED_OFF + 8 * 2 * RED_BOX_BYTES + 1024;
 };
+template <int BN, int EPI, bool TWO> constexpr int smem_bytes() { return EPI == EPI_F32_RED ? Cfg<BN, TWO>::RED_SMEM_BYTES : Cfg<BN, TWO>::SMEM_BYTES; }
 
 // Exact (erf) GELU.  1+erf(z) through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 output grid):
 //   z>=0: 2 - poly(t) e^{-z^2},  z<0: poly(t) e^{-z^2},  t = 1/(1 + 0.3275911 |z|)   -- one rcp, one ex2, 7 FMAs.
@@ -64,7 +70,7 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // remote arrive per epilogue warp.
 template <int BN, int EPI, bool MC, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
     using C = Cfg<BN, TWO>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -79,6 +85,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float* gamma_s = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
     pdl_launch_dependents();
+    // debug timeline (tools/gemm_timeline.py): per CTA, %globaltimer and clock64 at entry and exit in dbg[128 + 4 * blockIdx.x ...]
+    if (p.dbg && threadIdx.x == 0) {
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[128 + 4 * blockIdx.x] = t; p.dbg[128 + 4 * blockIdx.x + 1] = clock64();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_blocks = p.K / BK;
     // Work units: tiles (one CTA each), or with MC pairs of vertically adjacent tiles (one cluster each; an odd last row of tiles gets a
@@ -97,6 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if constexpr (EPI == EPI_F32_RED) tma_prefetch_desc(&tmC);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }   // TWO: both CTAs' epilogue warps
         mbar_fence_init();
@@ -233,13 +245,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
             uint32_t r[32];
 
-            if constexpr (EPI == EPI_F32 || EPI == EPI_F32_LN) {
+            if constexpr (EPI == EPI_F32_RED) {
+                // out32 += acc + bias, no residual read: thread = accumulator row writes its 32 columns of a chunk (+ bias, broadcast reads of
+                // this warp's private copy) as eight 16-byte pieces into a 32 x 128 B box, piece j of row r at position j ^ (r & 7) -- the TMA's
+                // 128-byte swizzle, conflict-free for the stores -- and one lane hands the box to the TMA as a bulk tensor reduction
+                // (UTMAREDG: the fp32 add happens in L2; rows past M are dropped by the tensor map).  Two boxes per warp: chunk c is built
+                // while the reduction of chunk c-1 still reads its box.
+                const int col0 = n0 + half * HC;
+                constexpr int NCH = HC / 32;
+                const uint32_t bias_s = smem_base + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + (warp - 2) * 512;     // 128 floats per warp
+                const uint32_t box0 = smem_base + C::RED_OFF + (warp - 2) * 2 * C::RED_BOX_BYTES;
+                __syncwarp();                                   // the previous tile's bias reads are done
+                {
+                    const float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + col0 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sts4(bias_s + lane * 16, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+                }
+                __syncwarp();
+                mbar_wait(tfull_bar(acc), acc_phase, 0x31);
+                tc_fence_after();
+                if (dbg_w) GEMM_TS(6);
+                const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    tmem_ld32(t_row + half * HC + c * 32, r);
+                    const uint32_t box = box0 + (c & 1) * C::RED_BOX_BYTES;
+                    if (lane == 0) bulk_wait_group_read<1>();   // the reduction issued two chunks ago has read this box
+                    __syncwarp();
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint4 b = lds4(bias_s + (c * 32 + 4 * k) * 4);
+                        sts4(box + lane * 128 + ((k ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * k]) + __uint_as_float(b.x)),
+                             __float_as_uint(__uint_as_float(r[4 * k + 1]) + __uint_as_float(b.y)),
+                             __float_as_uint(__uint_as_float(r[4 * k + 2]) + __uint_as_float(b.z)),
+                             __float_as_uint(__uint_as_float(r[4 * k + 3]) + __uint_as_float(b.w)));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmC, box, col0 + c * 32, row_base);
+                        bulk_commit_group();
+                    }
+                }
+            } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_LN) {
                 // Residual / static-embedding rows prefetched (coalesced) BEFORE waiting for the accumulator: the loads fly
                 // under this tile's MMAs.  Layout of ad[c][it]: chunk c (32 columns), rows rr0 + 4*it, 4 columns at cc*4.
                 // All addressing is hoisted: one 64-bit base per warp and tile, the loops only add compile-time multiples of the row
-                // pitch (the first version spent ~70 instructions per 16-byte store on row*ld + col in 64 bits; hoisting took the
-                // epilogue from 11.6 k to 10.3 k cycles per 128x256 tile, tools/gemm_timeline.py).  What remains is the memory system:
-                // all CTAs reach this phase together and move 128 KB in + 128 KB out each, ~4.8 TB/s through L2 during the burst.
+                // pitch.  What remains is the SM's store port: 31-32 B/clk per SM whatever the instruction (tools/microbench/store_rate.cu),
+                // 24 + 24 B/clk as load + store, so this 128 KB in + 128 KB out costs >= 5.4 k cycles; measured at speed 6.4 k
+                // (tools/gemm_timeline.py).  EPI_F32_RED above avoids the read in the SM and takes the same time.
                 const int col0 = n0 + half * HC;
                 constexpr int NCH = HC / 32;                 // 32-column chunks per warp
                 const int rows_left = p.M - (row_base + rr0);        // rows rr0 + 4*it with 4*it < rows_left exist
@@ -493,28 +547,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (EPI == EPI_F32_RED) {              // every reduction of this warp has completed before the CTA retires
+            if (lane == 0) bulk_wait_group<0>();
+            if (dbg_cta && dbg_w && lane == 0) p.dbg[15 * 8] = clock64();       // timeline: slot 7 = last reduction issued, this = all of them complete
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     if constexpr (PAIR) { cluster_arrive(); cluster_wait(); }   // no CTA leaves while its partner may still multicast into it / arrive on its barriers
     if (warp == 1) { if constexpr (TWO) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base); }
+    if (p.dbg && threadIdx.x == 0) {
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[128 + 4 * blockIdx.x + 2] = t; p.dbg[128 + 4 * blockIdx.x + 3] = clock64();
+    }
 }
 
 template <int BN, int EPI, bool MC = false, bool TWO = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
-    using C = Cfg<BN, TWO>;
+    constexpr int SMEM = smem_bytes<BN, EPI, TWO>();
     static bool configured = false;
     if (!configured) {
-        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
+    if constexpr (EPI == EPI_F32_RED)
+        RAP_REQUIRE(a.tm_out32 && a.addend == a.out32 && !a.table && !a.out16 && !a.conv_pitch,
+                    "gemm: the reduction epilogue is the in-place residual form (addend == out32, tm_out32 set, no table / fp16 shadow / convolution)");
+    const CUtensorMap& tmC = (EPI == EPI_F32_RED) ? *a.tm_out32 : tmA;      // unused by the other epilogues
     const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN;
-    ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
+    ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_F32_RED) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
     if constexpr (MC || TWO) {
         const int pairs = ((m_tiles + 1) / 2) * n_tiles;
         const int clusters = std::min(pairs, num_sms() / 2);
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, MC, TWO>, dim3(2 * clusters), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, MC, TWO>, dim3(2 * clusters), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a));
         note_launch();
         return RAP_OK;
     }
@@ -524,11 +590,11 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
         // one 128x256 tile per CTA, the two CTAs of a 128-row block (column halves) are a cluster: CTA rank = blockIdx.x & 1 = N-tile index
         RAP_REQUIRE(a.N == 2 * BN && a.ln_out && a.ln_mul && a.ln_add && a.ln_row_of_tok && !a.table && !a.out16 && !a.conv_pitch,
                     "gemm: the LayerNorm epilogue needs N = 512 and the ln_* arguments (no table / fp16 shadow / convolution)");
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, 2u, tmA, tmB, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a));
         note_launch();
         return RAP_OK;
     }
-    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, st, tmA, tmB, a));
+    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, tmA, tmB, tmC, a));
     note_launch();
     return RAP_OK;
 }
@@ -569,6 +635,7 @@ int launch_gemm(GemmEpi epi, int BN, const CUtensorMap& tmA, const CUtensorMap& 
             case EPI_QKV: return mc ? launch_t<256, EPI_QKV, true>(tmA, tmB, a, st) : launch_t<256, EPI_QKV>(tmA, tmB, a, st);
             case EPI_GEGLU: return mc ? launch_t<256, EPI_GEGLU, true>(tmA, tmB, a, st) : launch_t<256, EPI_GEGLU>(tmA, tmB, a, st);
             case EPI_F32_LN: return launch_t<256, EPI_F32_LN>(tmA, tmB, a, st);
+            case EPI_F32_RED: return launch_t<256, EPI_F32_RED>(tmA, tmB, a, st);
             default: break;
         }
     } else if (BN == 128) {

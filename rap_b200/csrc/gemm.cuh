@@ -17,6 +17,9 @@ enum GemmEpi : int {
                      // ln_out[row] = LN(out32[row]) * (ln_one_plus + ln_mul[sel(row)]) + ln_add[sel(row)].  N must be 512 = 2 tiles of 256: the
                      // two CTAs that own a 128-row block form a thread-block cluster and exchange per-row (sum, sum of squares) through
                      // distributed shared memory, so no LayerNorm kernel runs between the GEMMs (norm.py:76, layer.py:163)
+    EPI_F32_RED,     // out32 += acc + bias[col]: the in-place residual form of EPI_F32 (addend == out32) with NO residual read in the SM at all --
+                     // each epilogue warp writes (acc + bias) into a swizzled shared-memory box and hands it to the TMA as a bulk tensor
+                     // reduction (cp.reduce.async.bulk.tensor ... .add, fp32 add in L2).  Needs args.tm_out32 (fp32 map, 32x32 boxes).
 };
 
 struct GemmArgs {
@@ -31,6 +34,7 @@ struct GemmArgs {
     const float* gamma;       // EPI_QKV: [2(q,k), heads, 64]
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
+    const CUtensorMap* tm_out32;   // EPI_F32_RED: host pointer to the fp32 tensor map of out32 (make_tmap_f32_sw128, 32-row boxes); copied into the launch
     int mc;                   // pair modes: 0 = as RAP_GEMM_MC / RAP_GEMM_2CTA say (default off), 1 = B-tile multicast, 2 = plain, 3 = 2-CTA UMMA
     // EPI_F32_LN: modulation rows ln_mul / ln_add are selected per token, sel(row) = ln_row_of_tok[row] * ln_row_stride (AdaLN table row of the
     // token's scene; stride 0 + an all-zero index vector for the plain affine LayerNorm in front of the feed-forward block)

@@ -101,6 +101,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
         ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// Bulk tensor REDUCTION shared -> global: every element of the box is added (fp32 add in L2, type from the tensor map) to the tensor in
+// global memory; rows / columns of the box outside the tensor are dropped.  SASS: UTMAREDG.  Completion is tracked per thread through
+// bulk async-groups (commit / wait_group below), not through an mbarrier.
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// Bulk tensor store shared -> global (SASS: UTMASTG), same completion mechanism.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups still READING their shared-memory source / still incomplete
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Same, multicast: the box lands at the same shared-memory offset of every CTA of the cluster named in cta_mask, and each destination CTA's
 // mbarrier at that offset receives the complete_tx for the bytes written into ITS shared memory.
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t cta_mask) {

@@ -77,6 +77,30 @@ def test_gemm_f32_layernorm_epilogue(rap, M, K, in_place, per_row):
     assert err < 2e-2, f"max err {err}"
 
 
+@pytest.mark.parametrize("M,K,bias_on", [(8192, 512, True), (8192, 2048, True), (257, 128, True), (1000, 512, False), (128, 64, True), (40000, 512, True)])
+def test_gemm_f32_bulk_reduction_epilogue(rap, M, K, bias_on):
+    """EPI_F32_RED (5): the in-place residual GEMM h += A W^T + bias leaving through bulk tensor reductions (no residual read in the SM); ragged
+    last row tile (rows past M dropped by the tensor map), several tiles per CTA (40000 rows: 626 tiles on 148 CTAs), twice in a row
+    (the second launch accumulates on the first one's output)."""
+    g = torch.Generator("cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(512, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(512, device="cuda", generator=g) if bias_on else None
+    h0 = torch.randn(M + 64, 512, device="cuda", generator=g)          # 64 guard rows behind the tensor: must stay untouched
+    h = h0.clone()
+    upd = A.float() @ W.float().t() + (bias if bias_on else 0)
+    for rep in (1, 2):
+        rap.check(rap.lib.rap_test_gemm(5, 256, M, 512, K, A.data_ptr(), W.data_ptr(), rap.ptr(bias), h.data_ptr(), h.data_ptr(), None, None, None,
+                                        rap.stream_ptr()), "rap_test_gemm")
+        _sync_check(rap)
+        err = (h[:M] - (h0[:M] + rep * upd)).abs().max().item()
+        assert err < 2e-3 * rep, f"pass {rep}: max err {err}"
+        assert torch.equal(h[M:], h0[M:])
+    # bit-identical to the register epilogue up to the order of the two additions: (acc + bias) + h here, (acc + h) + bias there
+    ref32, _ = _gemm(rap, 0, 256, A, W, bias, h0[:M].contiguous())
+    assert (ref32 + upd - h[:M]).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("mode", [0x100, 0x300])
 @pytest.mark.parametrize("M", [8192, 257, 1000])
 def test_gemm_multicast_cluster_variant(rap, M, mode):

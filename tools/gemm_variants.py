@@ -19,4 +19,9 @@ for name, (epi, K, N) in {"qkv 512->1536": (2, 512, 1536), "out 512->512": (0, 5
                                                        _lib.ptr(o16), gamma.data_ptr() if epi == 2 else None, None, st), "gemm")
         ms = bench.timed(fn, 50, 5)
         row.append("%s %.1f us (%.0f TFLOP/s)" % ({0x200: "plain", 0x100: "multicast", 0x300: "2-CTA"}[mode], ms * 1e3, 2.0 * T * N * K / ms / 1e9))
+    if epi == 0:          # in-place residual form: register epilogue (addend = out) against the bulk-reduction epilogue (EPI_F32_RED = 5), alternating
+        for e in (0x200, 5, 0x200, 5):
+            fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e, 256, T, N, K, a.data_ptr(), w.data_ptr(), bias.data_ptr(), h.data_ptr(), h.data_ptr(), None, None, None, st), "gemm")
+            ms = bench.timed(fn, 50, 5)
+            row.append("%s %.1f us" % ("in-place" if e != 5 else "bulk-reduction", ms * 1e3))
     print(name + ": " + " | ".join(row), flush=True)
