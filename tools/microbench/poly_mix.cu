@@ -139,6 +139,71 @@ template <int QN, int QD> void runp() {
         printf("packed  poly %2d/%-2d warps/SMSP=%d : %.2f cycles per element per SMSP\n", QN, QD, threads / 128, (double)h / (iters * 32.0) / (threads / 128));
     }
 }
+// packed AND batched: the 16 pairs of a 32-element chunk go through every stage together (all the MUFUs of the chunk first, then the polynomial
+// pairs stage by stage), so that no instruction waits on the one in front of it -- the form a softmax warp with one partner per scheduler needs
+template <int QN, int QD> __global__ void kpb(float* out, long long* cyc, int iters, float c, float m) {
+    float x[32];
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    unsigned pk = 0;
+    for (int i = 0; i < 32; ++i) x[i] = -0.01f * (threadIdx.x % 13 + i);
+    const unsigned long long c2 = pk2(c, c), nm2 = pk2(-m, -m), magic = pk2(12582912.0f, 12582912.0f);
+    const unsigned long long k3 = pk2(0.077119089663028717f, 0.077119089663028717f), k2 = pk2(0.227564394474029541f, 0.227564394474029541f);
+    const unsigned long long k1 = pk2(0.695146143436431885f, 0.695146143436431885f), k0 = pk2(1.0f, 1.0f), eps = pk2(-1e-7f, -1e-7f), neg1 = pk2(-1.0f, -1.0f);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long u[16], r[16], f[16], e[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) u[j] = fma2(pk2(x[2 * j], x[2 * j + 1]), c2, nm2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) >= QN) {
+            float u0, u1, e0, e1; up2(u[j], u0, u1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u1));
+            e[j] = pk2(e0, e1);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) { float u0, u1; up2(u[j], u0, u1); u[j] = pk2(fmaxf(u0, -126.0f), fmaxf(u1, -126.0f)); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) r[j] = add2_rm(u[j], magic);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) f[j] = fma2(r[j], neg1, magic);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) f[j] = add2(u[j], f[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) e[j] = fma2(k3, f[j], k2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) e[j] = fma2(e[j], f[j], k1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) e[j] = fma2(e[j], f[j], k0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((j % QD) < QN) {
+            float p0, p1, r0, r1; up2(e[j], p0, p1); up2(r[j], r0, r1);
+            e[j] = pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc[j & 3] = add2(acc[j & 3], e[j]);
+            float e0, e1; up2(e[j], e0, e1);
+            __half2 h = __floats2half2_rn(e0, e1);
+            pk ^= *reinterpret_cast<unsigned*>(&h);
+            up2(add2(pk2(x[2 * j], x[2 * j + 1]), eps), x[2 * j], x[2 * j + 1]);
+        }
+    }
+    long long t1 = clock64();
+    float s = 0; for (int i = 0; i < 4; ++i) { float a, b; up2(acc[i], a, b); s += a + b; } for (int i = 0; i < 32; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s + __uint_as_float(pk);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+template <int QN, int QD> void runpb() {
+    float* d; long long* c; cudaMalloc(&d, 148 * 1024 * 4); cudaMalloc(&c, 8);
+    for (int threads : {128, 256, 512}) {
+        int iters = 2000;
+        kpb<QN, QD><<<148, threads>>>(d, c, 10, 0.18f, 1.0f);
+        kpb<QN, QD><<<148, threads>>>(d, c, iters, 0.18f, 1.0f);
+        long long h; cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+        printf("packed+batched poly %2d/%-2d warps/SMSP=%d : %.2f cycles per element per SMSP\n", QN, QD, threads / 128, (double)h / (iters * 32.0) / (threads / 128));
+    }
+}
 template <int QN, int QD> void runb() {
     float* d; long long* c; cudaMalloc(&d, 148 * 1024 * 4); cudaMalloc(&c, 8);
     for (int threads : {128, 256, 512}) {
@@ -170,6 +235,7 @@ __global__ void acc_check(float* err) {
 int main() {
     run<0, 4>(); run<1, 4>(); run<1, 1>();
     runp<0, 4>(); runp<1, 8>(); runp<1, 4>(); runp<5, 16>(); runp<3, 8>(); runp<1, 2>(); runp<1, 1>();
+    runpb<0, 8>(); runpb<1, 8>(); runpb<1, 4>(); runpb<3, 8>(); runpb<1, 2>(); runpb<1, 1>();
     float* e; cudaMalloc(&e, 4); cudaMemset(e, 0, 4); acc_check<<<1, 1024>>>(e); float h; cudaMemcpy(&h, e, 4, cudaMemcpyDeviceToHost);
     printf("poly max rel err on [-30,0.4]: %.3e\n", h);
     return 0;
