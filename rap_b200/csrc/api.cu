@@ -77,6 +77,14 @@ bool gemm_red() {
     return v == 1;
 }
 
+// RAP_GEGLU_SCALAR=1: the GEGLU epilogue's first form (scalar Abramowitz-Stegun erf, two MUFUs per output) for A/B runs; default is the
+// packed f32x2 form with erfc = 2^poly (gemm.cu geglu2).
+int geglu_act() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_GEGLU_SCALAR"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RAP_NO_PDL"); v = (e && atoi(e) == 1) ? 0 : 1; }
@@ -654,7 +662,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
             RAP_TRY(residual_gemm(o, pl->tm_attn16, d->tm_out[b][l], b == 0 ? 2 * l + 1 : -1 - l, true));   // + LN for the global block / the feed-forward
         }
         GemmArgs f1{};
-        f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER;
+        f1.M = T; f1.N = 2 * FF_INNER; f1.K = D; f1.bias = d->b1[l]; f1.out16 = pl->ffmid; f1.ld16 = FF_INNER; f1.act = geglu_act();
         RAP_TRY(launch_gemm(EPI_GEGLU, 256, pl->tm_x16, d->tm_w1[l], f1, st));
         GemmArgs f2{};
         f2.M = T; f2.N = D; f2.K = FF_INNER; f2.bias = d->b2[l]; f2.addend = pl->h; f2.out32 = pl->h; f2.ld32 = D;
@@ -855,6 +863,7 @@ extern "C" int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.out32 = out32; g.out16 = static_cast<__half*>(out16); g.gamma = gamma;
     g.mc = (epi >> 8) & 3;                                       // test hook: epi | 0x100 forces the multicast variant, | 0x200 forbids it
+    g.act = (epi >> 10) & 1;                                     // | 0x400: ReLU instead of SiLU (EPI_F16_SILU) / the scalar GELU form (EPI_GEGLU)
     epi &= 0xff;
     g.ld32 = N; g.ld16 = (epi == EPI_GEGLU) ? N / 2 : N; g.dbg = static_cast<long long*>(dbg);
     CUtensorMap tc;

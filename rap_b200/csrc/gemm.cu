@@ -57,6 +57,37 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// Two GEGLU outputs at once on packed f32x2 arithmetic: (h0, h1) * gelu((g0, g1)), exact-erf GELU through
+//   erfc(a) = 2^q(a),  q = degree-7 minimax fit of log2 erfc(|g| / sqrt 2) on |g| <= 5.94 (max |err| 9.5e-6 -> 6.6e-6 relative on erfc, also in
+//   the tail where 1 + erf underflows to erfc), so 1 + erf(g / sqrt 2) = E (g < 0), 2 - E (g >= 0), E = 2^q(min(|g|, 5.94)).
+// Beyond |g| = 5.94, E < 3e-9: gelu is g or 0 to fp16 precision.  Against the scalar Abramowitz-Stegun form this needs one MUFU per
+// output instead of two and 10 issue slots instead of 22 (8 FFMA2 + 2 FADD2 + 2 FMUL2 per PAIR): with two epilogue warps per scheduler the
+// scalar version (5.2-6.0 k cycles per 128x256 tile) was longer than the tile's K loop (4.8-5.0 k), i.e. this GEMM was bound by its epilogue.
+__device__ __forceinline__ uint32_t geglu2(f32x2 h, f32x2 g) {
+    float g0, g1;
+    unpack2(g, g0, g1);
+    const f32x2 a = pack2(fminf(fabsf(g0), 5.94f), fminf(fabsf(g1), 5.94f));
+    f32x2 q = ffma2(pack2(-1.833969122e-06f, -1.833969122e-06f), a, pack2(6.158401811e-05f, 6.158401811e-05f));
+    q = ffma2(q, a, pack2(-9.304317646e-04f, -9.304317646e-04f));
+    q = ffma2(q, a, pack2(8.507597260e-03f, 8.507597260e-03f));
+    q = ffma2(q, a, pack2(-5.395960808e-02f, -5.395960808e-02f));
+    q = ffma2(q, a, pack2(-4.584647417e-01f, -4.584647417e-01f));
+    q = ffma2(q, a, pack2(-1.151250958e+00f, -1.151250958e+00f));
+    q = ffma2(q, a, pack2(4.702056685e-06f, 4.702056685e-06f));
+    float q0, q1;
+    unpack2(q, q0, q1);
+    const float e0 = ex2f(q0), e1 = ex2f(q1);
+    // half of (1 + erf): 0.5 + copysign(0.5 - 0.5 E, g)
+    float u0, u1;
+    unpack2(ffma2(pack2(e0, e1), pack2(-0.5f, -0.5f), pack2(0.5f, 0.5f)), u0, u1);
+    u0 = __uint_as_float(__float_as_uint(u0) | (__float_as_uint(g0) & 0x80000000u));
+    u1 = __uint_as_float(__float_as_uint(u1) | (__float_as_uint(g1) & 0x80000000u));
+    const f32x2 w = fadd2(pack2(u0, u1), pack2(0.5f, 0.5f));
+    float o0, o1;
+    unpack2(fmul2(fmul2(h, g), w), o0, o1);
+    return pack_half2(o0, o1);
+}
+
 // MC (multicast): the kernel runs as 2-CTA clusters whose CTAs own vertically adjacent 128-row tiles of the SAME column tile.  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicast into both CTAs' stage (cp.async.bulk.tensor ... .multicast::cluster), so the weight
 // operand crosses the L2 -> SM fabric once per pair instead of once per CTA.  The K loops of these GEMMs are bound by exactly that traffic
@@ -498,13 +529,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tmem_ld_wait();
                             const float* bh = p.bias + n0 + c * 32;
                             const float* bg = p.bias + n0 + BN / 2 + c * 32;
+                            if (p.act == 1) {                   // A/B: the scalar Abramowitz-Stegun epilogue (RAP_GEGLU_SCALAR=1)
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 h4 = *reinterpret_cast<const float4*>(bh + i), g4 = *reinterpret_cast<const float4*>(bg + i);
+                                    pk[cp * 16 + i / 2] = pack_half2((__uint_as_float(r[i]) + h4.x) * gelu_erf(__uint_as_float(r2[i]) + g4.x),
+                                                                     (__uint_as_float(r[i + 1]) + h4.y) * gelu_erf(__uint_as_float(r2[i + 1]) + g4.y));
+                                    pk[cp * 16 + i / 2 + 1] = pack_half2((__uint_as_float(r[i + 2]) + h4.z) * gelu_erf(__uint_as_float(r2[i + 2]) + g4.z),
+                                                                         (__uint_as_float(r[i + 3]) + h4.w) * gelu_erf(__uint_as_float(r2[i + 3]) + g4.w));
+                                }
+                                continue;
+                            }
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
                                 const float4 h4 = *reinterpret_cast<const float4*>(bh + i), g4 = *reinterpret_cast<const float4*>(bg + i);
-                                pk[cp * 16 + i / 2] = pack_half2((__uint_as_float(r[i]) + h4.x) * gelu_erf(__uint_as_float(r2[i]) + g4.x),
-                                                                 (__uint_as_float(r[i + 1]) + h4.y) * gelu_erf(__uint_as_float(r2[i + 1]) + g4.y));
-                                pk[cp * 16 + i / 2 + 1] = pack_half2((__uint_as_float(r[i + 2]) + h4.z) * gelu_erf(__uint_as_float(r2[i + 2]) + g4.z),
-                                                                     (__uint_as_float(r[i + 3]) + h4.w) * gelu_erf(__uint_as_float(r2[i + 3]) + g4.w));
+                                pk[cp * 16 + i / 2] = geglu2(fadd2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), pack2(h4.x, h4.y)),
+                                                             fadd2(pack2(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1])), pack2(g4.x, g4.y)));
+                                pk[cp * 16 + i / 2 + 1] = geglu2(fadd2(pack2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), pack2(h4.z, h4.w)),
+                                                                 fadd2(pack2(__uint_as_float(r2[i + 2]), __uint_as_float(r2[i + 3])), pack2(g4.z, g4.w)));
                             }
                         }
                     }

@@ -13,7 +13,7 @@ def run(name, epi, bn, M, N, K):
     bias = torch.randn(N, device="cuda"); add = torch.randn(M, N, device="cuda") if epi in (0, 5) else None
     gamma = torch.ones(2, 8, 64, device="cuda")
     out32 = (add if epi in (0, 5) else None)          # in place, as in the sampler
-    out16 = torch.zeros(M, N, device="cuda", dtype=torch.float16) if epi not in (0, 5) else None
+    out16 = torch.zeros(M, N, device="cuda", dtype=torch.float16) if (epi & 0xff) not in (0, 5) else None
     dbg = torch.zeros(128 + 4 * 160, dtype=torch.int64, device="cuda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     def launch():
@@ -34,7 +34,7 @@ def run(name, epi, bn, M, N, K):
     print(f"== {name}: M={M} N={N} K={K} BN={bn}: {us:.2f} us per launch back to back ({2*M*N*K/us/1e6:.0f} TFLOP/s), SM clock {ghz:.2f} GHz, {len(ctas)} CTAs")
     print(f"  CTA entry us min/median/max {e.min():.2f}/{np.median(e):.2f}/{e.max():.2f}; exit {x.min():.2f}/{np.median(x):.2f}/{x.max():.2f}; "
           f"lifetime median {np.median(x-e):.2f} max {np.max(x-e):.2f}; kernel span {x.max():.2f} -> launch-to-launch gap {us - x.max():.2f} us")
-    for t in range(2 if epi in (0, 5) else 4):
+    for t in range(2 if (epi & 0xff) in (0, 5) else 4):
         r = tl[t]
         if r[0] == 0: break
         print(f"  CTA 0 tile{t} (cycles from CTA entry {r[0]-ctas[0][1]}): prod [{r[0]-t0},{r[1]-t0}]  mma wait_acc {r[3]-r[2]} issue_span {r[4]-r[3]} (start {r[2]-t0})  epi start {r[5]-t0} acc_ready {r[6]-t0} done {r[7]-t0} (epi work {r[7]-r[6]})")
@@ -49,3 +49,4 @@ if not os.environ.get("F32_ONLY"):
     run("ff2 f32 bn128", 0, 128, 8192, 512, 2048)
     run("qkv rmsnorm", 2, 256, 8192, 1536, 512)
     run("geglu", 3, 256, 8192, 4096, 512)
+    run("geglu, scalar gelu epilogue", 3 | 0x400, 256, 8192, 4096, 512)
