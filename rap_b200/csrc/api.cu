@@ -85,6 +85,12 @@ int geglu_act() {
     return v;
 }
 
+int qkv_act() {                                             // RAP_QKV_SCALAR=1: scalar RMS-norm epilogue of the QKV GEMM (A/B)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RAP_QKV_SCALAR"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("RAP_NO_PDL"); v = (e && atoi(e) == 1) ? 0 : 1; }
@@ -648,7 +654,7 @@ int dit_body(rap_plan* pl, const float* x, int tab_row0, bool per_scene, cudaStr
     for (int l = 0; l < d->L; ++l) {
         for (int b = 0; b < 2; ++b) {
             GemmArgs q{};
-            q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l];
+            q.M = T; q.N = 3 * D; q.K = D; q.out16 = pl->qkv; q.ld16 = 3 * D; q.gamma = d->gamma[b][l]; q.act = qkv_act();
             RAP_TRY(launch_gemm(EPI_QKV, 256, pl->tm_x16, d->tm_qkv[b][l], q, st));
             FmhaArgs f{};
             f.items = b == 0 ? pl->items_part : pl->items_batch; f.cta_ptr = b == 0 ? pl->cta_ptr_part : pl->cta_ptr_batch; f.ws = pl->fmha_ws; f.counters = pl->fmha_counters;

@@ -498,11 +498,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tmem_ld32(t_row + hc * 64, r);
                         tmem_ld32(t_row + hc * 64 + 32, r2);
                         tmem_ld_wait();
-                        if (section < 2) {
+                        if (section < 2 && p.act == 1) {            // A/B: the scalar form (RAP_QKV_SCALAR=1)
                             float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int i = 0; i < 32; ++i) { const float a = __uint_as_float(r[i]), b = __uint_as_float(r2[i]); ss[i & 3] += a * a + b * b; }
-                            const float inv = 8.0f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
+                            const float inv = 8.0f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
                             const float4* g4 = reinterpret_cast<const float4*>(gamma_s + (section * 8 + head) * 64);
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
@@ -511,6 +511,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 pk[i / 2 + 1] = pack_half2(__uint_as_float(r[i + 2]) * inv * g0.z, __uint_as_float(r[i + 3]) * inv * g0.w);
                                 pk[16 + i / 2] = pack_half2(__uint_as_float(r2[i]) * inv * g1.x, __uint_as_float(r2[i + 1]) * inv * g1.y);
                                 pk[16 + i / 2 + 1] = pack_half2(__uint_as_float(r2[i + 2]) * inv * g1.z, __uint_as_float(r2[i + 3]) * inv * g1.w);
+                            }
+                        } else if (section < 2) {
+                            // packed f32x2 arithmetic: half the issue slots of the scalar form (the epilogue warps share their schedulers with
+                            // the UMMA-issuing and the TMA warp; a lighter epilogue also shortens the K loop it overlaps, tools/gemm_timeline.py)
+                            f32x2 ss2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                const f32x2 a = pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), b = pack2(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
+                                ss2[(i >> 1) & 1] = ffma2(a, a, ss2[(i >> 1) & 1]);
+                                ss2[2 + ((i >> 1) & 1)] = ffma2(b, b, ss2[2 + ((i >> 1) & 1)]);
+                            }
+                            float s0, s1;
+                            unpack2(fadd2(fadd2(ss2[0], ss2[1]), fadd2(ss2[2], ss2[3])), s0, s1);
+                            const float inv = 8.0f / fmaxf(sqrtf(s0 + s1), 1e-12f);     // F.normalize eps, * sqrt(head_dim)
+                            const f32x2 inv2 = pack2(inv, inv);
+                            const float4* g4 = reinterpret_cast<const float4*>(gamma_s + (section * 8 + head) * 64);
+                            auto scaled = [&](uint32_t x0, uint32_t x1, float ga, float gb) {
+                                float o0, o1;
+                                unpack2(fmul2(fmul2(pack2(__uint_as_float(x0), __uint_as_float(x1)), inv2), pack2(ga, gb)), o0, o1);
+                                return pack_half2(o0, o1);
+                            };
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 g0 = g4[i / 4], g1 = g4[8 + i / 4];
+                                pk[i / 2] = scaled(r[i], r[i + 1], g0.x, g0.y);
+                                pk[i / 2 + 1] = scaled(r[i + 2], r[i + 3], g0.z, g0.w);
+                                pk[16 + i / 2] = scaled(r2[i], r2[i + 1], g1.x, g1.y);
+                                pk[16 + i / 2 + 1] = scaled(r2[i + 2], r2[i + 3], g1.z, g1.w);
                             }
                         } else {
 #pragma unroll

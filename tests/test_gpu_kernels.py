@@ -131,13 +131,15 @@ def test_gemm_silu_f16(rap):
     assert (out16.float() - ref).abs().max().item() < 1e-2
 
 
-def test_gemm_qkv_rmsnorm(rap):
+@pytest.mark.parametrize("scalar", [0, 1])
+def test_gemm_qkv_rmsnorm(rap, scalar):
+    """scalar=0: the product's packed f32x2 epilogue; 1: the scalar form kept for A/B runs (epi | 0x400)."""
     g = torch.Generator("cuda").manual_seed(2)
     M = 700
     A = torch.randn(M, 512, device="cuda", generator=g).half()
     W = (torch.randn(1536, 512, device="cuda", generator=g) / 22).half()
     gamma = 1 + 0.1 * torch.randn(2, 8, 64, device="cuda", generator=g)
-    _, out16 = _gemm(rap, 2, 256, A, W, gamma=gamma)
+    _, out16 = _gemm(rap, 2 | (0x400 if scalar else 0), 256, A, W, gamma=gamma)
     qkv = (A.float() @ W.float().t()).view(M, 3, 8, 64)
     q = F.normalize(qkv[:, 0], dim=-1) * gamma[0] * 8
     k = F.normalize(qkv[:, 1], dim=-1) * gamma[1] * 8

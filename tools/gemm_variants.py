@@ -19,6 +19,11 @@ for name, (epi, K, N) in {"qkv 512->1536": (2, 512, 1536), "out 512->512": (0, 5
                                                        _lib.ptr(o16), gamma.data_ptr() if epi == 2 else None, None, st), "gemm")
         ms = bench.timed(fn, 50, 5)
         row.append("%s %.1f us (%.0f TFLOP/s)" % ({0x200: "plain", 0x100: "multicast", 0x300: "2-CTA"}[mode], ms * 1e3, 2.0 * T * N * K / ms / 1e9))
+    if epi == 2:          # QKV epilogue: packed f32x2 RMS-norm against the scalar form (| 0x400), alternating
+        for e in (2, 2 | 0x400, 2, 2 | 0x400):
+            fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e | 0x200, 256, T, N, K, a.data_ptr(), w.data_ptr(), None, None, None, o16.data_ptr(), gamma.data_ptr(), None, st), "gemm")
+            ms = bench.timed(fn, 50, 5)
+            row.append("%s %.1f us" % ("packed norm" if e == 2 else "scalar norm", ms * 1e3))
     if epi == 3:          # GEGLU epilogue: packed f32x2 erfc = 2^poly form against the scalar Abramowitz-Stegun one (| 0x400), alternating
         for e in (3, 3 | 0x400, 3, 3 | 0x400):
             fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e | 0x200, 256, T, N, K, a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, None, o16.data_ptr(), None, None, st), "gemm")
