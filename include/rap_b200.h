@@ -173,7 +173,8 @@ const char* rap_profile_class_name(int kernel_class);
 /* Micro entry points used by tests/ and profiling to exercise one kernel at a time.  rap_test_gemm: epi = 0 f32 bias+residual, 1 f16 SiLU,
  * 2 QKV + RMS-norm, 3 GEGLU, 5 the in-place residual form out32 += A W^T + bias through bulk tensor reductions (addend must equal out32, no out16);
  * epi | 0x100 runs the 2-CTA-cluster variant that shares the weight tile by TMA multicast (BN = 256), | 0x300 the 2-CTA UMMA variant, | 0x200
- * forbids both (default: RAP_GEMM_MC / RAP_GEMM_2CTA, off).  dbg: NULL or a device buffer of 128 + 4 * 148 int64 (clock64 timeline of CTA 0 in
+ * forbids both (default: RAP_GEMM_MC / RAP_GEMM_2CTA, off); | 0x400 ReLU (epi 1) / the scalar epilogue forms (epi 2, 3); | 0x800 fp16 tiles written by
+ * bulk tensor stores (epi 2, 3).  dbg: NULL or a device buffer of 128 + 4 * 148 int64 (clock64 timeline of CTA 0 in
  * [tile][8], then per CTA {globaltimer, clock64} at entry and exit). */
 int rap_test_gemm(int epi, int bn, int M, int N, int K, const void* A_f16, const void* W_f16, const float* bias,
                   const float* addend, float* out32, void* out16, const float* gamma, void* dbg, void* stream);

@@ -41,7 +41,11 @@ template <int BN, bool TWO = false> struct Cfg {
     static constexpr int RED_OFF = (STG_OFF + 1023) & ~1023;
     static constexpr int RED_SMEM_BYTES = RED_OFF + 8 * 2 * RED_BOX_BYTES + 1024;
 };
-template <int BN, int EPI, bool TWO> constexpr int smem_bytes() { return EPI == EPI_F32_RED ? Cfg<BN, TWO>::RED_SMEM_BYTES : Cfg<BN, TWO>::SMEM_BYTES; }
+// EPI_QKV / EPI_GEGLU on plain 256-wide tiles may leave through bulk tensor STORES (GemmArgs::tm_out16): the same two boxes per warp.
+template <int BN, int EPI, bool TWO, bool MC = false> constexpr bool tma16_capable() { return (EPI == EPI_QKV || EPI == EPI_GEGLU) && BN == 256 && !TWO && !MC; }
+template <int BN, int EPI, bool TWO, bool MC = false> constexpr int smem_bytes() {
+    return (EPI == EPI_F32_RED || tma16_capable<BN, EPI, TWO, MC>()) ? Cfg<BN, TWO>::RED_SMEM_BYTES : Cfg<BN, TWO>::SMEM_BYTES;
+}
 
 // Exact (erf) GELU.  1+erf(z) through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 output grid):
 //   z>=0: 2 - poly(t) e^{-z^2},  z<0: poly(t) e^{-z^2},  t = 1/(1 + 0.3275911 |z|)   -- one rcp, one ex2, 7 FMAs.
@@ -130,8 +134,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     const int num_tiles = PAIR ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    auto tile_m0 = [&](int tile) { return (PAIR ? 2 * (tile / n_tiles) + (int)crank : tile / n_tiles) * BM; };
-    auto tile_n0 = [&](int tile) { return (tile % n_tiles) * BN; };
+    // raster = 0: consecutive tiles walk the columns of one row block (neighbouring CTAs share the A tile); 1: they walk the row blocks of one
+    // column tile (neighbours share the weight tile).  Plain tiles only.
+    const bool col_major = !PAIR && p.raster == 1;
+    auto tile_m0 = [&](int tile) { return (PAIR ? 2 * (tile / n_tiles) + (int)crank : col_major ? tile % m_tiles : tile / n_tiles) * BM; };
+    auto tile_n0 = [&](int tile) { return (col_major ? tile / m_tiles : tile % n_tiles) * BN; };
     constexpr int B_BOXES = BN / 128 > 0 ? BN / 128 : 1;      // the B tensor map has 128-row boxes (BN = 256: two per stage)
     constexpr int B_BOX_ROWS = BN < 128 ? BN : 128;
     constexpr int B_BOX_BYTES = B_BOX_ROWS * BK * 2;
@@ -139,7 +146,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if constexpr (EPI == EPI_F32_RED) tma_prefetch_desc(&tmC);
+        if (EPI == EPI_F32_RED || (tma16_capable<BN, EPI, TWO, MC>() && p.tma16)) tma_prefetch_desc(&tmC);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TWO ? 16 : 8); }   // TWO: both CTAs' epilogue warps
         mbar_fence_init();
@@ -268,6 +275,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             return v;
         };
         const bool dbg_w = warp == 2;
+        uint32_t box_sel = 0;                                 // bulk-store epilogues: which of this warp's two boxes is next
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++dbg_tile) {
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
@@ -578,6 +586,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                     }
+                    if (tma16_capable<BN, EPI, TWO, MC>() && p.tma16) {
+                        // 64 fp16 outputs of this thread's row = one 128-byte row of a 32-row box in the TMA's 128-byte swizzle (16-byte piece k of
+                        // row r at position k ^ (r & 7): conflict-free stores, no transposing read-back), handed to the TMA as one bulk tensor
+                        // store (UTMASTG); rows past M are dropped by the tensor map.  Two boxes per warp alternate.
+                        const uint32_t box = smem_base + C::RED_OFF + ((warp - 2) * 2 + (int)(box_sel & 1u)) * C::RED_BOX_BYTES;
+                        ++box_sel;
+                        if (lane == 0) bulk_wait_group_read<1>();      // the store issued two rounds ago has read this box
+                        __syncwarp();
+                        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sts4(box + lane * 128 + ((k ^ sw) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, box, out_col, row_base);
+                            bulk_commit_group();
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) sts4(stg_w + k * 16, pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
                     __syncwarp();
@@ -617,7 +644,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (EPI == EPI_F32_RED) {              // every reduction of this warp has completed before the CTA retires
+        if (EPI == EPI_F32_RED || (tma16_capable<BN, EPI, TWO, MC>() && p.tma16)) {   // every bulk reduction / store of this warp has completed before the CTA retires
             if (lane == 0) bulk_wait_group<0>();
             if (dbg_cta && dbg_w && lane == 0) p.dbg[15 * 8] = clock64();       // timeline: slot 7 = last reduction issued, this = all of them complete
         }
@@ -635,7 +662,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int BN, int EPI, bool MC = false, bool TWO = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
-    constexpr int SMEM = smem_bytes<BN, EPI, TWO>();
+    constexpr int SMEM = smem_bytes<BN, EPI, TWO, MC>();
     static bool configured = false;
     if (!configured) {
         RAP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, MC, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -644,13 +671,15 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
     if constexpr (EPI == EPI_F32_RED)
         RAP_REQUIRE(a.tm_out32 && a.addend == a.out32 && !a.table && !a.out16 && !a.conv_pitch,
                     "gemm: the reduction epilogue is the in-place residual form (addend == out32, tm_out32 set, no table / fp16 shadow / convolution)");
-    const CUtensorMap& tmC = (EPI == EPI_F32_RED) ? *a.tm_out32 : tmA;      // unused by the other epilogues
+    GemmArgs a2 = a;
+    a2.tma16 = (tma16_capable<BN, EPI, TWO, MC>() && a.tm_out16 && !a.conv_pitch) ? 1 : 0;
+    const CUtensorMap& tmC = (EPI == EPI_F32_RED) ? *a.tm_out32 : a2.tma16 ? *a.tm_out16 : tmA;      // unused by the other epilogues
     const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN;
     ProfScope _ps((EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_F32_RED) ? KC_GEMM_F32 : EPI == EPI_F16_SILU ? KC_GEMM_SILU : EPI == EPI_QKV ? KC_GEMM_QKV : KC_GEMM_GEGLU, st);
     if constexpr (MC || TWO) {
         const int pairs = ((m_tiles + 1) / 2) * n_tiles;
         const int clusters = std::min(pairs, num_sms() / 2);
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, MC, TWO>, dim3(2 * clusters), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, MC, TWO>, dim3(2 * clusters), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a2));
         note_launch();
         return RAP_OK;
     }
@@ -660,11 +689,11 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
         // one 128x256 tile per CTA, the two CTAs of a 128-row block (column halves) are a cluster: CTA rank = blockIdx.x & 1 = N-tile index
         RAP_REQUIRE(a.N == 2 * BN && a.ln_out && a.ln_mul && a.ln_add && a.ln_row_of_tok && !a.table && !a.out16 && !a.conv_pitch,
                     "gemm: the LayerNorm epilogue needs N = 512 and the ln_* arguments (no table / fp16 shadow / convolution)");
-        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a));
+        RAP_CUDA(launch_pdl_cluster(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, 2u, tmA, tmB, tmC, a2));
         note_launch();
         return RAP_OK;
     }
-    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, tmA, tmB, tmC, a));
+    RAP_CUDA(launch_pdl(gemm_kernel<BN, EPI, false>, dim3(grid), dim3(kThreads), SMEM, st, tmA, tmB, tmC, a2));
     note_launch();
     return RAP_OK;
 }

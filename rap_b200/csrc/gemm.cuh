@@ -35,6 +35,10 @@ struct GemmArgs {
     int act;                  // EPI_F16_SILU: 0 = SiLU, 1 = ReLU
     long long* dbg;           // optional clock64() timeline of CTA 0: [tile][8] (tools/gemm_timeline.py), else null
     const CUtensorMap* tm_out32;   // EPI_F32_RED: host pointer to the fp32 tensor map of out32 (make_tmap_f32_sw128, 32-row boxes); copied into the launch
+    const CUtensorMap* tm_out16;   // EPI_QKV / EPI_GEGLU (plain 256-wide tiles): host pointer to the fp16 tensor map of out16 with 32-row boxes
+                                   // (make_tmap_f16_sw128(..., 32)) -> the epilogue leaves through bulk tensor stores; null = per-thread stores
+    int tma16;                     // set by launch_gemm
+    int raster;                    // tile order of the plain kernels: 0 = row-block major (default), 1 = column-tile major
     int mc;                   // pair modes: 0 = as RAP_GEMM_MC / RAP_GEMM_2CTA say (default off), 1 = B-tile multicast, 2 = plain, 3 = 2-CTA UMMA
     // EPI_F32_LN: modulation rows ln_mul / ln_add are selected per token, sel(row) = ln_row_of_tok[row] * ln_row_stride (AdaLN table row of the
     // token's scene; stride 0 + an all-zero index vector for the plain affine LayerNorm in front of the feed-forward block)

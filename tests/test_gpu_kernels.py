@@ -131,15 +131,16 @@ def test_gemm_silu_f16(rap):
     assert (out16.float() - ref).abs().max().item() < 1e-2
 
 
-@pytest.mark.parametrize("scalar", [0, 1])
+@pytest.mark.parametrize("scalar", [0, 1, 2])
 def test_gemm_qkv_rmsnorm(rap, scalar):
-    """scalar=0: the product's packed f32x2 epilogue; 1: the scalar form kept for A/B runs (epi | 0x400)."""
+    """scalar=0: the product's packed f32x2 epilogue; 1: the scalar form kept for A/B runs (epi | 0x400); 2: packed, tiles written by bulk tensor
+    stores (epi | 0x800; 700 rows = a ragged last tile, clipped by the tensor map)."""
     g = torch.Generator("cuda").manual_seed(2)
     M = 700
     A = torch.randn(M, 512, device="cuda", generator=g).half()
     W = (torch.randn(1536, 512, device="cuda", generator=g) / 22).half()
     gamma = 1 + 0.1 * torch.randn(2, 8, 64, device="cuda", generator=g)
-    _, out16 = _gemm(rap, 2 | (0x400 if scalar else 0), 256, A, W, gamma=gamma)
+    _, out16 = _gemm(rap, 2 | {0: 0, 1: 0x400, 2: 0x800}[scalar], 256, A, W, gamma=gamma)
     qkv = (A.float() @ W.float().t()).view(M, 3, 8, 64)
     q = F.normalize(qkv[:, 0], dim=-1) * gamma[0] * 8
     k = F.normalize(qkv[:, 1], dim=-1) * gamma[1] * 8
@@ -147,7 +148,7 @@ def test_gemm_qkv_rmsnorm(rap, scalar):
     assert (out16.float() - ref).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("scalar", [0, 1])
+@pytest.mark.parametrize("scalar", [0, 1, 2])
 def test_gemm_geglu(rap, scalar):
     """GEGLU epilogue: h * gelu(g), exact-erf GELU.  scalar=0: the product's packed f32x2 form (erfc = 2^poly, one MUFU per output); 1: the
     scalar Abramowitz-Stegun form kept for A/B runs (epi | 0x400).  Gate values are scaled so that the tails (|g| up to ~9) are exercised."""
@@ -159,7 +160,7 @@ def test_gemm_geglu(rap, scalar):
     bias = 0.1 * torch.randn(4096, device="cuda", generator=g)
     # pack rows the way rap_dit_load_weight does: per 256-row tile = 128 h rows then the matching 128 g rows
     idx = torch.cat([torch.cat([torch.arange(t * 128, t * 128 + 128), 2048 + torch.arange(t * 128, t * 128 + 128)]) for t in range(16)]).cuda()
-    _, out16 = _gemm(rap, 3 | (0x400 if scalar else 0), 256, A, W[idx].contiguous(), bias[idx].contiguous(), out16_cols=2048)
+    _, out16 = _gemm(rap, 3 | {0: 0, 1: 0x400, 2: 0x800}[scalar], 256, A, W[idx].contiguous(), bias[idx].contiguous(), out16_cols=2048)   # 2: bulk tensor stores
     hg = A.double() @ W.double().t() + bias
     ref = hg[:, :2048] * F.gelu(hg[:, 2048:])
     err = (out16.double() - ref).abs()

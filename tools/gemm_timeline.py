@@ -50,3 +50,6 @@ if not os.environ.get("F32_ONLY"):
     run("qkv rmsnorm", 2, 256, 8192, 1536, 512)
     run("geglu", 3, 256, 8192, 4096, 512)
     run("geglu, scalar gelu epilogue", 3 | 0x400, 256, 8192, 4096, 512)
+    run("qkv rmsnorm, bulk tensor stores", 2 | 0x800, 256, 8192, 1536, 512)
+    run("geglu, bulk tensor stores", 3 | 0x800, 256, 8192, 4096, 512)
+    run("qkv rmsnorm, bulk tensor stores, column-major tiles", 2 | 0x1800, 256, 8192, 1536, 512)

@@ -20,15 +20,15 @@ for name, (epi, K, N) in {"qkv 512->1536": (2, 512, 1536), "out 512->512": (0, 5
         ms = bench.timed(fn, 50, 5)
         row.append("%s %.1f us (%.0f TFLOP/s)" % ({0x200: "plain", 0x100: "multicast", 0x300: "2-CTA"}[mode], ms * 1e3, 2.0 * T * N * K / ms / 1e9))
     if epi == 2:          # QKV epilogue: packed f32x2 RMS-norm against the scalar form (| 0x400), alternating
-        for e in (2, 2 | 0x400, 2, 2 | 0x400):
+        for e in (2, 2 | 0x400, 2 | 0x800, 2 | 0x1800, 2, 2 | 0x400, 2 | 0x800, 2 | 0x1800):
             fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e | 0x200, 256, T, N, K, a.data_ptr(), w.data_ptr(), None, None, None, o16.data_ptr(), gamma.data_ptr(), None, st), "gemm")
             ms = bench.timed(fn, 50, 5)
-            row.append("%s %.1f us" % ("packed norm" if e == 2 else "scalar norm", ms * 1e3))
+            row.append("%s %.1f us" % ({2: "packed norm", 2 | 0x400: "scalar norm", 2 | 0x800: "packed + bulk stores", 2 | 0x1800: "+ column-major tiles"}[e], ms * 1e3))
     if epi == 3:          # GEGLU epilogue: packed f32x2 erfc = 2^poly form against the scalar Abramowitz-Stegun one (| 0x400), alternating
-        for e in (3, 3 | 0x400, 3, 3 | 0x400):
+        for e in (3, 3 | 0x400, 3 | 0x800, 3 | 0x1800, 3, 3 | 0x400, 3 | 0x800, 3 | 0x1800):
             fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e | 0x200, 256, T, N, K, a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, None, o16.data_ptr(), None, None, st), "gemm")
             ms = bench.timed(fn, 50, 5)
-            row.append("%s %.1f us" % ("packed gelu" if e == 3 else "scalar gelu", ms * 1e3))
+            row.append("%s %.1f us" % ({3: "packed gelu", 3 | 0x400: "scalar gelu", 3 | 0x800: "packed + bulk stores", 3 | 0x1800: "+ column-major tiles"}[e], ms * 1e3))
     if epi == 0:          # in-place residual form: register epilogue (addend = out) against the bulk-reduction epilogue (EPI_F32_RED = 5), alternating
         for e in (0x200, 5, 0x200, 5):
             fn = lambda: _lib.check(_lib.lib.rap_test_gemm(e, 256, T, N, K, a.data_ptr(), w.data_ptr(), bias.data_ptr(), h.data_ptr(), h.data_ptr(), None, None, None, st), "gemm")
