@@ -94,14 +94,13 @@ __device__ __forceinline__ uint32_t geglu2(f32x2 h, f32x2 g) {
 
 // MC (multicast): the kernel runs as 2-CTA clusters whose CTAs own vertically adjacent 128-row tiles of the SAME column tile.  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicast into both CTAs' stage (cp.async.bulk.tensor ... .multicast::cluster), so the weight
-// operand crosses the L2 -> SM fabric once per pair instead of once per CTA.  The K loops of these GEMMs are bound by exactly that traffic
-// ((128 + 256) rows x 128 B per 128x256x64 step at ~42 B/clk/SM of L2 bandwidth when every SM streams, against 512 tensor-pipe cycles), see
-// DESIGN.md.  A stage is free again when BOTH CTAs have consumed it: the empty barriers count two arrivals and every UMMA commit arrives on
+// operand crosses the L2 -> SM fabric once per pair instead of once per CTA (the premise -- K loops bound by that traffic -- turned out wrong:
+// the TMA delivers a 48 KB stage per 214-227 ns on all SMs, the K loops take 375-384 ns per step because of the stage round trip, DESIGN.md
+// 5.2).  A stage is free again when BOTH CTAs have consumed it: the empty barriers count two arrivals and every UMMA commit arrives on
 // the barrier of both CTAs (tcgen05.commit ... .multicast::cluster).
 // TWO (2-CTA UMMA, `cta_group::2`): the same pair of vertically adjacent tiles runs as ONE 256x256 UMMA.  Each CTA keeps its own A tile
-// and only ITS half of the B tile in shared memory (32 KB per stage instead of 48: the K loop of these GEMMs is bound by what an SM can
-// ingest); the even CTA of the pair issues the MMAs for both, each CTA's accumulator rows land in its own TMEM, and the epilogues are
-// untouched.  Loads of both CTAs are counted on the even CTA's stage barrier, stage / accumulator hand-backs are multicast commits and one
+// and only ITS half of the B tile in shared memory (32 KB per stage instead of 48); the even CTA of the pair issues the MMAs for both, each
+// CTA's accumulator rows land in its own TMEM, and the epilogues are untouched.  Loads of both CTAs are counted on the even CTA's stage barrier, stage / accumulator hand-backs are multicast commits and one
 // remote arrive per epilogue warp.
 template <int BN, int EPI, bool MC, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -700,8 +699,9 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, 
 
 // RAP_GEMM_MC=1: 2-CTA clusters share the B tile by multicast.  Built, parity-tested and measured (r02, same-box alternating A/B, 3 rounds):
 // 99.59 / 99.66 / 99.50 ms per pair with it, 99.46 / 99.56 / 99.54 without; in isolation 2-10 % SLOWER (QKV 16.6 vs 15.9 us, out-proj 10.3 vs
-// 9.4).  It removes 27 % of the L2 reads (ncu lts__throughput 37.9 % -> 27.6 % on the GEGLU GEMM) but not one byte of what each SM has to
-// ingest, which is what bounds the K loop, and it couples the two CTAs' pipelines.  Hence off by default.
+// 9.4).  It removes 27 % of the L2 reads (ncu lts__throughput 37.9 % -> 27.6 % on the GEGLU GEMM) but the K loop is bound by the round trip of
+// a stage (commit -> producer -> 360-400 ns of load latency -> MMAs; three stages = 375-384 ns per step), not by L2 or SM bandwidth (the TMA
+// alone delivers a 48 KB stage per 214-227 ns on all SMs, tools/microbench/load_rate.cu), and it couples the two CTAs' pipelines.  Off by default.
 // RAP_GEMM_2CTA=1: pairs of CTAs run 256x256 UMMAs with `cta_group::2` (each SM ingests half of the weight tile).
 bool gemm_two_cta() {
     static int v = -1;
