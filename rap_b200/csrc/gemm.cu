@@ -644,7 +644,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI == EPI_F32_RED || (tma16_capable<BN, EPI, TWO, MC>() && p.tma16)) {   // every bulk reduction / store of this warp has completed before the CTA retires
-            if (lane == 0) bulk_wait_group<0>();
+            // .read: the boxes have been read out of shared memory (the CTA may retire); the global writes themselves complete with the grid,
+            // like per-thread stores, and waiting for them here only lengthens the tail of latency-bound launches
+            if (lane == 0) bulk_wait_group_read<0>();
             if (dbg_cta && dbg_w && lane == 0) p.dbg[15 * 8] = clock64();       // timeline: slot 7 = last reduction issued, this = all of them complete
         }
     }
